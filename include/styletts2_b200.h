@@ -1,0 +1,207 @@
+/* styletts2_b200 -- C ABI of the B200 (sm_100a) StyleTTS 2 inference hot path.
+ *
+ * The reference (yl4579/StyleTTS2) is pure Python/PyTorch and has no FFI: the calls this
+ * library replaces are the ATen operator calls inside the reference's nn.Module.forward
+ * methods.  Each entry point below cites the reference call site(s) it stands in for.
+ * The Python host side (styletts2_b200/*.py) binds these with ctypes and keeps the
+ * reference's module names, forward signatures and state-dict keys.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to fp32 (or int32/int64 where said), owned by the
+ *    caller; nothing is allocated or freed here; no hidden synchronisation;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it;
+ *  - activations are [B, C, L] with L contiguous ("conv layout") or row-major
+ *    [rows, features] ("row layout"); batch strides are in ELEMENTS;
+ *  - return value: 0 on success, else a cudaError_t value; st2_last_error() describes it.
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef STYLETTS2_B200_H
+#define STYLETTS2_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST2_ABI_VERSION 1
+
+/* activation codes (prologue / epilogue selectors) */
+#define ST2_ACT_NONE 0
+#define ST2_ACT_LRELU 1 /* F.leaky_relu(x, slope) */
+#define ST2_ACT_SNAKE 2 /* x + sin(alpha x)^2 / alpha, alpha per channel */
+#define ST2_ACT_TANH 3
+#define ST2_ACT_GELU 4 /* exact erf GELU (nn.GELU default) */
+
+const char* st2_last_error(void);
+int st2_abi_version(void);
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+long long st2_launch_count(void);
+
+/* ------------------------------------------------------------------ weight preparation
+ * torch.nn.utils.weight_norm (dim=0): w[r,:] = v[r,:] * g[r] / ||v[r,:]||_2
+ * (re-evaluated every forward by the reference: Modules/istftnet.py:30-46, models.py:293;
+ * here folded once at load). */
+int st2_weight_norm_fold(const float* v, const float* g, float* w, int rows, int cols, void* stream);
+/* Conv1d weight [Cout,Cin,K] -> kernel layout [Cin][K][Cout] */
+int st2_conv_weight_layout(const float* w, float* wt, int Cout, int Cin, int K, void* stream);
+/* ConvTranspose1d weight [Cin,Cout,K] (stride S, padding P) -> polyphase layout
+ * [S][Cin][J][Cout], J = ceil(K/S): phase r is a J-tap stride-1 conv (see st2_conv_transpose1d). */
+int st2_convT_weight_layout(const float* w, float* wp, int Cin, int Cout, int K, int S, int P, void* stream);
+
+/* ------------------------------------------------------------------ fused Conv1d
+ * y[b,co,oidx(q)] = epi( bias[co] + sum_{ci,k} W[co,ci,k] * pre(x[b,ci, q*stride + k*dil - pad]) )
+ *   pre(v) = act_pre(a[b,ci]*v + b[b,ci])  (AdaIN affine, then LeakyReLU / Snake); zero outside [0,Lin)
+ *   epi(v) = act_out( accum( (v + res[b,co, oidx >> res_shift]) / out_div ) )
+ * and optionally per-(b,co) partial statistics (count, mean, M2) of the stored values for the
+ * NEXT InstanceNorm (fixed-order, deterministic; merged by st2_adain_coef).
+ * Replaces: F.conv1d call sites of Modules/istftnet.py:70,73,361,377,445-448,511-517,
+ * Modules/hifigan.py:69-72,330,344, models.py:293,390-395,506-510 together with the
+ * AdaIN1d / Snake / LeakyReLU / residual / MRF-mean elementwise ops around them. */
+typedef struct st2_conv_args {
+  const float* x;         /* [B, Cin, Lin] */
+  long long x_bstride;    /* elements between utterances */
+  int Cin, Lin;
+  const float* w;         /* [Cin][K][Cout] (st2_conv_weight_layout) */
+  const float* bias;      /* [Cout] or NULL */
+  float* y;               /* rows of length y_len */
+  long long y_bstride;
+  int Cout;
+  int Lq;                 /* number of output positions q computed */
+  int y_len;              /* row length of y */
+  int y_tstride, y_toffset; /* oidx = q*y_tstride + y_toffset */
+  int B, K, stride, dil, pad;
+  const float* pre_a;     /* [B,Cin] or NULL (no affine) */
+  const float* pre_b;
+  int pre_act;            /* ST2_ACT_NONE / LRELU / SNAKE */
+  float pre_slope;
+  const float* pre_alpha; /* [Cin] for SNAKE */
+  const float* res;       /* residual rows of length res_len, or NULL */
+  long long res_bstride;
+  int res_len, res_shift;
+  float out_div;          /* 1.0 if unused; (res+sc)/sqrt(2) of AdainResBlk1d (models.py:415) */
+  int accum_mode;         /* 0: y=v   1: y+=v   2: y=(y+v)/accum_div  (MRF mean, istftnet.py:369-375) */
+  float accum_div;
+  int out_act;            /* ST2_ACT_NONE / ST2_ACT_TANH */
+  float* stats;           /* [B,Cout,stats_nparts,3] or NULL */
+  int stats_nparts, stats_part_offset;
+  int dup_q0_to;          /* >=0: the q==0 value is also stored at that index (reflection pad, istftnet.py:366) */
+} st2_conv_args;
+int st2_conv1d(const st2_conv_args* a, void* stream);
+/* number of stats partials st2_conv1d writes for Lq outputs */
+int st2_conv_stats_parts(int Lq);
+
+/* ConvTranspose1d (stride S, K taps, padding P; output length Lin*S) as S polyphase
+ * stride-1 convolutions through the same fused kernel; `a` describes the x / y / prologue /
+ * epilogue exactly as for st2_conv1d with K,stride,dil,pad,Lq,y_tstride,y_toffset,w ignored;
+ * wp is the st2_convT_weight_layout buffer.  reflect_left1 != 0 implements
+ * ReflectionPad1d((1,0)) on the output (istftnet.py:365-366): y has Lin*S+1 columns.
+ * stats needs room for S*st2_conv_stats_parts(Lin) partials.
+ * Replaces: Generator.ups[i] (istftnet.py:364, hifigan.py:333). */
+int st2_conv_transpose1d(const st2_conv_args* a, const float* wp, int K, int S, int P, int reflect_left1, void* stream);
+
+/* ------------------------------------------------------------------ InstanceNorm / AdaIN
+ * per-(b,c) (count, mean, M2) over L for a tensor not produced by st2_conv1d. */
+int st2_instance_stats(const float* x, long long bstride, int B, int C, int L, float* stats, void* stream);
+/* AdaIN1d coefficients (Modules/istftnet.py:15-25, models.py:349-359): merges the partials
+ * (Chan, fp64), biased variance, eps; a=(1+gamma)*rstd, b=beta-mean*a with gamma=gb[b, c],
+ * beta=gb[b, C+c] (gb row stride gb_stride). */
+int st2_adain_coef(const float* stats, int nparts, const float* gb, long long gb_stride, int B, int C,
+                   float eps, float* a, float* b, void* stream);
+/* residual path of an upsampling AdainResBlk1d (models.py:404-407): y[b,c,:2L] =
+ * depthwise ConvTranspose1d(k3,s2,p1,op1)(lrelu_0.2(a*x+b)) with weight pw[C,3], bias pb[C]. */
+int st2_adain_lrelu_pool(const float* x, long long x_bstride, const float* a, const float* b, const float* pw,
+                         const float* pb, float slope, int B, int C, int L, float* y, long long y_bstride, void* stream);
+/* TextEncoder block tail (models.py:270-282,295-296,310): LayerNorm over CHANNELS of a
+ * [B,C,L] tensor, LeakyReLU(slope), zero where t >= lengths[b] (lengths may be NULL). in place ok. */
+int st2_channel_layernorm_lrelu(const float* x, float* y, const float* gamma, const float* beta, float eps,
+                                float slope, const int* lengths, int B, int C, int L, void* stream);
+
+/* ------------------------------------------------------------------ row-layout ops (denoiser, duration encoder)
+ * For each row r=(b,n), width C:
+ *   h = (h_in ? h_in[r,:] : [xs * x[b,0:Cx] | emb[r,0:C-Cx]]) + (add ? add[b,:] : 0);  h_out[r,:] = h (if h_out)
+ *   z = LayerNorm(h) (eps);  out1 = z*(g1 (+1 if ada)) + b1;  out2 likewise (if out2)
+ *   g/b are [C] vectors (gb_bstride==0) or per-utterance rows (gb_bstride = row stride).
+ * Replaces: modules.py:392-397 (x cat/expand, x+mapping), 556-557 (norm, norm_context),
+ * 18-38 (AdaLayerNorm), models.py:418-438. */
+typedef struct st2_rows_args {
+  const float* h_in; long long h_in_ld;
+  const float* x; int Cx; float xs; const float* emb; long long emb_ld;
+  const float* add;       /* [B,C] or NULL */
+  float* h_out; long long h_out_ld;
+  const float* g1; const float* b1; const float* g2; const float* b2; long long gb_bstride; int ada;
+  float* out1; long long out1_ld; float* out2; long long out2_ld;
+  int B, N, C; float eps;
+  const int* lengths;     /* rows n >= lengths[b] are written as zeros (masked_fill), may be NULL */
+} st2_rows_args;
+int st2_rows_ln(const st2_rows_args* a, void* stream);
+/* dst[(b,n), col0 + j] = (n < lengths[b]) ? src[b, j] : 0   (style concat, models.py:539-541,551-552) */
+int st2_bcast_cols(float* dst, long long ld, int col0, const float* src, int B, int N, int W, const int* lengths, void* stream);
+/* out[b,:] = mean_n h[(b,n),:]  (modules.py:399) */
+int st2_mean_rows(const float* h, long long ld, int B, int N, int C, float* out, void* stream);
+
+/* C[M,Nf] = act(A W^T + bias) + R.  A element (m,k): A + (m / a_L)*a_bs + (m % a_L)*a_ls + k*a_ks
+ * (row layout: a_L=M, a_ls=K, a_ks=1; conv layout [B,K,L]: a_L=L, a_bs=K*L, a_ls=1, a_ks=L).
+ * W is [Nf,K] row-major (torch Linear / conv1x1 weight).  Replaces every nn.Linear on the path
+ * (modules.py:256-261,484-490,521,333-338; models.py:674,451; LSTM input projections). */
+int st2_linear(const float* A, long long a_bs, long long a_ls, long long a_ks, int a_L, const float* W,
+               const float* bias, const float* R, long long ldr, float* C, long long ldc, int M, int Nf, int K,
+               int act, void* stream);
+
+/* Multi-head attention without mask (modules.py:523-535): q [B*N, H*D], kv [B*N, 2*H*D]
+ * (k | v), out [B*N, H*D]; softmax(q k^T * scale) v per (b,h). D must be 64. */
+int st2_attention(const float* q, const float* kv, float* out, int B, int N, int H, int D, float scale, void* stream);
+
+/* Bidirectional single-layer LSTM recurrence (models.py:300,450,453,523; gate order i,f,g,o).
+ * gx [B*L, 8H] = x W_ih^T + b_ih + b_hh for (fwd | bwd); whh [2][4H][H]; out element
+ * (b,t,dir*H+j) at out + b*o_bs + t*o_ts + (dir*H+j)*o_cs.  lengths (int32 [B]) or NULL gives
+ * pack_padded_sequence semantics (backward pass starts at lengths[b]-1; padded steps = 0).
+ * work: >= 6*B*H floats of scratch. */
+int st2_lstm_bidir(const float* gx, const float* whh, float* out, long long o_bs, long long o_ts, long long o_cs,
+                   const int* lengths, int B, int L, int H, float* work, void* stream);
+
+/* ------------------------------------------------------------------ sampler (sampler.py:193-208,497-510)
+ * d = (x_eval - (c_skip*x_eval + c_out*x_pred)) / sigma_eval;  out = x_base + d*dt (+ eps*sigma_up).
+ * If x_pred_masked != NULL: x_pred := masked + (x_pred - masked)*cfg_scale first (modules.py:420-423). */
+int st2_kdiff_step(const float* x_eval, const float* x_pred, const float* x_pred_masked, float cfg_scale,
+                   float c_skip, float c_out, float sigma_eval, const float* x_base, float dt, const float* eps,
+                   float sigma_up, float* out, int n, void* stream);
+/* out = a*x (c_in scaling, sampler.py:205) */
+int st2_scale(const float* x, float a, float* out, int n, void* stream);
+/* LearnedPositionalEmbedding (modules.py:657-671): out[b,:] = [t, sin(2 pi w t), cos(2 pi w t)], w [half] */
+int st2_time_embedding(const float* t /* [B] */, const float* w, int half, int B, float* out, long long ld, void* stream);
+/* out = a*x + b*y (style blending alpha/beta, Inference_LibriTTS.ipynb#cell16) */
+int st2_axpby(const float* x, float a, const float* y, float b, float* out, int n, void* stream);
+
+/* ------------------------------------------------------------------ text / duration glue
+ * out[b,c,n] = (n < lengths[b]) ? table[tokens[b,n], c] : 0   (models.py:303-306) */
+int st2_embedding_cl(const long long* tokens, const float* table, const int* lengths, int B, int N, int C, float* out, void* stream);
+/* pred_dur[b,n] = max(1, rint(sum_j sigmoid(logits[b,n,j]))) (+last_plus on n==N-1)  -- integer boundary
+ * (Inference_LJSpeech.ipynb#cell17).  dur_f (optional) receives the pre-rounding sums. */
+int st2_durations(const float* logits, int B, int N, int J, int last_plus, int* pred_dur, float* dur_f, void* stream);
+/* frame -> token map from durations: tok[b,t] for t < T (T = row length), exclusive scan per utterance;
+ * frames beyond sum(dur[b]) map to the last token.  total[b] = sum(dur[b]). */
+int st2_frame_tokens(const int* dur, int B, int N, int T, int shift_right, int* tok, int* total, void* stream);
+/* alignment expansion (d^T @ aln, t_en @ aln; #cell17) as a gather:
+ *  rows: out[(b,t), c] = src[(b,tok[b,t]), c]      src row layout [B*N, C] (ld)
+ *  cl  : out[b,c,t]    = src[b,c,tok[b,t]]         src conv layout [B,C,N] */
+int st2_expand_rows(const float* src, long long src_ld, const int* tok, int B, int N, int T, int C, float* out, long long out_ld, void* stream);
+int st2_expand_cl(const float* src, const int* tok, int B, int C, int N, int T, float* out, long long out_bstride, void* stream);
+
+/* ------------------------------------------------------------------ harmonic source + (i)STFT
+ * SineGen + SourceModuleHnNSF (istftnet.py:146-247,283-297 == hifigan.py:117-218,254-268):
+ * f0 [B,F] (F = 2T frames), nearest-upsampled by `scale`; 9 harmonics; fp64 phase accumulation as
+ * torch.cumsum on CPU; linear interpolation with PyTorch's align_corners=False rule;
+ * uv = f0 > 10; noise [B, F*scale, 9] = the randn_like draw (istftnet.py:242), injected;
+ * lin_w [9], lin_b [1] = m_source.l_linear; out [B, F*scale] = tanh(linear(.)). */
+int st2_sine_source(const float* f0, int B, int F, int scale, const float* noise, const float* lin_w,
+                    const float* lin_b, float* out, float* phase_work /* B*9*F floats */, void* stream);
+/* TorchSTFT.transform (istftnet.py:91-97): n_fft 20, hop 5, hann, center/reflect.
+ * x [B,L] -> har [B,22,L/5+1] = [|X| ; angle X]. */
+int st2_stft20(const float* x, int B, int L, float* har, void* stream);
+/* conv_post tail + TorchSTFT.inverse (istftnet.py:378-380,99-104): x [B,22,Fr] ->
+ * spec=exp(x[:11]), phase=sin(x[11:]) -> istft (n_fft 20, hop 5) -> wav [B, 5*(Fr-1)]. */
+int st2_istft20_expsin(const float* x, int B, int Fr, float* wav, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,112 @@
+// Bidirectional LSTM recurrence (fp32).  The input projection x W_ih^T + b is one batched GEMM
+// (st2_linear) done beforehand; this file runs the serial part: for every step,
+//   gates = gx[:, t] + h_{t-1} W_hh^T ; (i,f,g,o) ; c = f*c + i*g ; h = o*tanh(c)
+// v1: one launch per time step covering both directions (grid.y) and all utterances; a CTA owns
+// 4 hidden units x 32 utterances, stages its 16 W_hh rows and the 32 previous hidden vectors in
+// shared memory and does 128-bit conflict-free reads.  The sequential depth (N token steps,
+// T frame steps) makes this latency-bound, not bandwidth-bound.
+#include "common.cuh"
+
+namespace st2 {
+extern long long g_launches;
+
+constexpr int LSTM_UT = 4;   // hidden units per CTA
+constexpr int LSTM_BT = 32;  // utterances per CTA
+
+__global__ void __launch_bounds__(LSTM_UT* LSTM_BT) lstm_step_kernel(
+    const float* __restrict__ gx, const float* __restrict__ whh, float* __restrict__ out, long long o_bs, long long o_ts,
+    long long o_cs, const int* __restrict__ lengths, int B, int L, int H, int step, const float* __restrict__ h_prev,
+    float* __restrict__ h_next, float* __restrict__ c_state) {
+  extern __shared__ __align__(16) float sm[];
+  const int HP = H + 4;
+  float* ws = sm;                       // [4 gates][UT][HP]
+  float* hs = sm + 4 * LSTM_UT * HP;    // [BT][HP]
+  const int dir = blockIdx.y;
+  const int j0 = blockIdx.x * LSTM_UT;
+  const int b0 = blockIdx.z * LSTM_BT;
+  const int tid = threadIdx.x;
+  const float* wd = whh + (long long)dir * 4 * H * H;
+  for (int i = tid; i < 4 * LSTM_UT * H; i += blockDim.x) {
+    const int k = i % H;
+    const int r = i / H;  // g*UT + u
+    const int g = r / LSTM_UT, u = r - g * LSTM_UT;
+    ws[r * HP + k] = (j0 + u < H) ? wd[((long long)g * H + j0 + u) * H + k] : 0.f;
+  }
+  const float* hp = h_prev + (long long)dir * B * H;
+  for (int i = tid; i < LSTM_BT * H; i += blockDim.x) {
+    const int k = i % H, bl = i / H;
+    hs[bl * HP + k] = (b0 + bl < B) ? hp[(long long)(b0 + bl) * H + k] : 0.f;
+  }
+  __syncthreads();
+  const int u = tid % LSTM_UT, bl = tid / LSTM_UT;
+  const int b = b0 + bl, j = j0 + u;
+  if (b >= B || j >= H) return;
+  const int len = lengths ? lengths[b] : L;
+  float* hn = h_next + (long long)dir * B * H + (long long)b * H + j;
+  if (step >= len) {  // padded step: state carried through unchanged, no output
+    *hn = hs[bl * HP + j];
+    return;
+  }
+  const int t = dir == 0 ? step : (len - 1 - step);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const float* hr = hs + bl * HP;
+  const float* w0 = ws + (0 * LSTM_UT + u) * HP;
+  const float* w1 = ws + (1 * LSTM_UT + u) * HP;
+  const float* w2 = ws + (2 * LSTM_UT + u) * HP;
+  const float* w3 = ws + (3 * LSTM_UT + u) * HP;
+#pragma unroll 4
+  for (int k = 0; k < H; k += 4) {
+    const float4 hv = *reinterpret_cast<const float4*>(hr + k);
+    const float4 x0 = *reinterpret_cast<const float4*>(w0 + k);
+    const float4 x1 = *reinterpret_cast<const float4*>(w1 + k);
+    const float4 x2 = *reinterpret_cast<const float4*>(w2 + k);
+    const float4 x3 = *reinterpret_cast<const float4*>(w3 + k);
+    a0 = fmaf(hv.x, x0.x, a0); a0 = fmaf(hv.y, x0.y, a0); a0 = fmaf(hv.z, x0.z, a0); a0 = fmaf(hv.w, x0.w, a0);
+    a1 = fmaf(hv.x, x1.x, a1); a1 = fmaf(hv.y, x1.y, a1); a1 = fmaf(hv.z, x1.z, a1); a1 = fmaf(hv.w, x1.w, a1);
+    a2 = fmaf(hv.x, x2.x, a2); a2 = fmaf(hv.y, x2.y, a2); a2 = fmaf(hv.z, x2.z, a2); a2 = fmaf(hv.w, x2.w, a2);
+    a3 = fmaf(hv.x, x3.x, a3); a3 = fmaf(hv.y, x3.y, a3); a3 = fmaf(hv.z, x3.z, a3); a3 = fmaf(hv.w, x3.w, a3);
+  }
+  const float* g = gx + ((long long)b * L + t) * (8 * H) + (long long)dir * 4 * H + j;
+  const float gi = sigmoidf_(g[0] + a0);
+  const float gf = sigmoidf_(g[H] + a1);
+  const float gg = tanhf(g[2 * H] + a2);
+  const float go = sigmoidf_(g[3 * H] + a3);
+  float* cp = c_state + (long long)dir * B * H + (long long)b * H + j;
+  const float c = gf * (*cp) + gi * gg;
+  *cp = c;
+  const float h = go * tanhf(c);
+  *hn = h;
+  out[(long long)b * o_bs + (long long)t * o_ts + (long long)(dir * H + j) * o_cs] = h;
+}
+
+}  // namespace st2
+
+using namespace st2;
+
+extern "C" int st2_lstm_bidir(const float* gx, const float* whh, float* out, long long o_bs, long long o_ts, long long o_cs,
+                              const int* lengths, int B, int L, int H, float* work, void* stream) {
+  ST2_REQUIRE(gx && whh && out && work && B > 0 && L > 0 && H > 0 && H % 4 == 0, "st2_lstm_bidir", "bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)2 * B * H;
+  float* h0 = work;
+  float* h1 = work + n;
+  float* c = work + 2 * n;
+  cudaError_t e = cudaMemsetAsync(work, 0, 3 * n * sizeof(float), st);
+  if (e != cudaSuccess) { set_error("st2_lstm_bidir", e); return (int)e; }
+  const size_t smem = (size_t)(4 * LSTM_UT + LSTM_BT) * (H + 4) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  ST2_REQUIRE(smem <= 160 * 1024, "st2_lstm_bidir", "hidden size too large");
+  dim3 grid(cdiv(H, LSTM_UT), 2, cdiv(B, LSTM_BT));
+  for (int s = 0; s < L; ++s) {
+    const float* hp = (s & 1) ? h1 : h0;
+    float* hn = (s & 1) ? h0 : h1;
+    lstm_step_kernel<<<grid, LSTM_UT * LSTM_BT, smem, st>>>(gx, whh, out, o_bs, o_ts, o_cs, lengths, B, L, H, s, hp, hn, c);
+    ++g_launches;
+  }
+  ST2_CHECK_LAUNCH("st2_lstm_bidir");
+  return 0;
+}

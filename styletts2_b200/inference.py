@@ -1,0 +1,106 @@
+"""Text(tokens) -> waveform glue with the Demo notebooks' semantics, batched.
+
+Follows Demo/Inference_LJSpeech.ipynb#cell17 (`inference(text, noise, diffusion_steps, embedding_scale)`)
+and Demo/Inference_LibriTTS.ipynb#cell16 (`inference(text, ref_s, alpha, beta, ...)`): text encoder ->
+bert_encoder -> style diffusion sampler -> duration encoder / duration head -> integer durations ->
+alignment expansion (gather) -> F0Ntrain -> decoder.  PL-BERT's output `bert_dur` and the token ids
+are inputs (phonemizer / PL-BERT are outside the accelerated path).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .diffusion import ADPM2Sampler, DiffusionSampler, KarrasSchedule
+from .models import Munch
+
+
+def length_to_mask(lengths):
+    """utils.py:42-45"""
+    mask = torch.arange(int(lengths.max()), device=lengths.device).unsqueeze(0).expand(lengths.shape[0], -1).type_as(lengths)
+    return torch.gt(mask + 1, lengths.unsqueeze(1))
+
+
+def make_sampler(model):
+    """notebook cell 14"""
+    return DiffusionSampler(model.diffusion.diffusion, sampler=ADPM2Sampler(),
+                            sigma_schedule=KarrasSchedule(sigma_min=0.0001, sigma_max=3.0, rho=9.0), clamp=False)
+
+
+class Synthesizer:
+    """Batched, equal-length text->waveform engine over a build_model() container (on one GPU)."""
+
+    def __init__(self, model: Munch, model_cfg, device="cuda"):
+        self.model, self.cfg, self.device = model, model_cfg, torch.device(device)
+        self.multispeaker = bool(model_cfg["multispeaker"])
+        self.hifigan = model_cfg["decoder"]["type"] == "hifigan"
+        self.sampler = make_sampler(model)
+
+    @torch.no_grad()
+    def synthesize(self, tokens, input_lengths, bert_dur, noise, *, diffusion_steps=5, embedding_scale=1.0, ref_s=None,
+                   alpha=0.3, beta=0.7, rng: Optional[Dict] = None, forced_durations=None, pin_frames_per_token=None,
+                   return_all=False):
+        """tokens [B,N] i64, input_lengths [B], bert_dur [B,N,768], noise [B,1,256] (device tensors).
+        rng (parity mode): 'step_noises' list of [B,1,256], 'sine_noise' [B,L,9], 'har' [B,22,F].
+        forced_durations [B,N] int: teacher-forced durations (after the duration kernel has run).
+        pin_frames_per_token: throughput mode of SURVEY section 8d (durations pinned so that T = N*k)."""
+        m = self.model
+        rng = rng or {}
+        dev = self.device
+        B, N = tokens.shape
+        mask = length_to_mask(input_lengths)
+        t_en = m.text_encoder(tokens, input_lengths, mask)                       # [B,512,N]
+        d_en_rows = m.bert_encoder(bert_dur)                                      # [B,N,512]
+        kw = dict(embedding=bert_dur, num_steps=diffusion_steps, embedding_scale=embedding_scale,
+                  step_noises=rng.get("step_noises"))
+        if self.multispeaker:
+            kw["features"] = ref_s
+        s_pred = self.sampler(noise, **kw).reshape(B, 256)
+        s = s_pred[:, 128:]
+        ref = s_pred[:, :128]
+        if self.multispeaker:
+            ref = ops.axpby(ref, alpha, ref_s[:, :128], 1 - alpha)
+            s = ops.axpby(s, beta, ref_s[:, 128:], 1 - beta)
+        s, ref = s.contiguous(), ref.contiguous()
+        d = m.predictor.text_encoder(d_en_rows.transpose(-1, -2), s, input_lengths, mask)   # [B,N,640]
+        x, _ = m.predictor.lstm(d)
+        logits = m.predictor.duration_proj(x)                                     # [B,N,50]
+        pred_dur, dur_f = ops.durations(logits, 0 if self.multispeaker else 5)
+        if forced_durations is not None:
+            use = forced_durations.to(device=dev, dtype=torch.int32).contiguous()
+        elif pin_frames_per_token is not None:
+            use = torch.full((B, N), int(pin_frames_per_token), device=dev, dtype=torch.int32)
+        else:
+            use = pred_dur
+        totals = use.sum(dim=1)
+        T = int(totals.max().item())        # the one host sync of the path: buffer sizes depend on it
+        if not bool((totals == T).all()):
+            raise ValueError("batched synthesis needs equal total durations; run ragged utterances one by one")
+        tok, _ = ops.frame_tokens(use, T, shift_right=self.hifigan)
+        en_rows = ops.expand_rows(d, tok)                                         # [B,T,640]
+        asr = ops.expand_cl(t_en, tok)                                            # [B,512,T]
+        F0, Ncurve = m.predictor.F0Ntrain(en_rows.transpose(-1, -2), s)
+        wav = m.decoder(asr, F0, Ncurve, ref, sine_noise=rng.get("sine_noise"), har=rng.get("har"))
+        out = dict(wav=wav, pred_dur=pred_dur, T=T)
+        if return_all:
+            out.update(t_en=t_en, d_en=d_en_rows.transpose(-1, -2), s_pred=s_pred, s=s, ref=ref, d=d, logits=logits,
+                       dur_f=dur_f, en=en_rows.transpose(-1, -2), asr=asr, F0=F0, N=Ncurve)
+        return out
+
+    @torch.no_grad()
+    def inference(self, tokens: List[int], bert_dur, noise=None, ref_s=None, alpha=0.3, beta=0.7, diffusion_steps=5,
+                  embedding_scale=1.0):
+        """Single-utterance call with the notebooks' conventions: `tokens` already cleaned (TextCleaner) with
+        the leading 0; returns a numpy waveform (LibriTTS variant trims the last 50 samples)."""
+        dev = self.device
+        tk = torch.tensor([list(tokens)], dtype=torch.long, device=dev)
+        lens = torch.tensor([tk.shape[1]], dtype=torch.long, device=dev)
+        if noise is None:
+            noise = torch.randn(1, 1, 256, device=dev)
+        out = self.synthesize(tk, lens, bert_dur.to(dev), noise.to(dev), diffusion_steps=diffusion_steps,
+                              embedding_scale=embedding_scale, ref_s=None if ref_s is None else ref_s.to(dev),
+                              alpha=alpha, beta=beta)
+        wav = out["wav"].squeeze().cpu().numpy()
+        return wav[..., :-50] if self.multispeaker else wav

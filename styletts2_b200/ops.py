@@ -1,0 +1,361 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point family).
+
+torch is used for device memory (allocation through the caching allocator) and streams only;
+every arithmetic op on the path is a kernel of libstyletts2_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib as L
+from .lib import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SNAKE, ACT_TANH, ConvArgs, RowsArgs, ptr, stream_ptr
+
+f32 = torch.float32
+
+
+def _cl(x: torch.Tensor) -> torch.Tensor:
+    """Require conv layout [B,C,L] with contiguous rows (batch stride free)."""
+    assert x.dim() == 3 and x.dtype == f32
+    if x.stride(2) != 1 or x.stride(1) != x.shape[2]:
+        x = x.contiguous()
+    return x
+
+
+def empty(*shape, device, dtype=f32):
+    return torch.empty(shape, device=device, dtype=dtype)
+
+
+# ------------------------------------------------------------------ weight preparation
+def fold_weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    rows = v.shape[0]
+    v2 = v.detach().contiguous().view(rows, -1)
+    w = torch.empty_like(v2)
+    L.call("st2_weight_norm_fold", ptr(v2), ptr(g.detach().contiguous()), ptr(w), rows, v2.shape[1], stream_ptr())
+    return w.view_as(v)
+
+
+def conv_weight_layout(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,Cin,K] -> [Cin,K,Cout]"""
+    w = w.detach().contiguous()
+    co, ci, k = w.shape
+    wt = empty(ci, k, co, device=w.device)
+    L.call("st2_conv_weight_layout", ptr(w), ptr(wt), co, ci, k, stream_ptr())
+    return wt
+
+
+def convT_weight_layout(w: torch.Tensor, stride: int, padding: int) -> torch.Tensor:
+    """[Cin,Cout,K] -> [S,Cin,J,Cout]"""
+    w = w.detach().contiguous()
+    ci, co, k = w.shape
+    j = (k + stride - 1) // stride
+    wp = empty(stride, ci, j, co, device=w.device)
+    L.call("st2_convT_weight_layout", ptr(w), ptr(wp), ci, co, k, stride, padding, stream_ptr())
+    return wp
+
+
+# ------------------------------------------------------------------ conv
+def stats_parts(lq: int) -> int:
+    return (lq + 255) // 256
+
+
+def _fill_conv_args(a: ConvArgs, x, wt, bias, y, *, K, stride, dil, pad, Lq, y_len, pre, pre_act, slope, alpha, res,
+                    res_shift, out_div, accum_mode, accum_div, out_act, stats, nparts):
+    B, Cin, Lin = x.shape
+    a.x, a.x_bstride, a.Cin, a.Lin = ptr(x), x.stride(0), Cin, Lin
+    a.w, a.bias = ptr(wt), ptr(bias)
+    a.y, a.y_bstride, a.Cout, a.Lq, a.y_len = ptr(y), y.stride(0), y.shape[1], Lq, y_len
+    a.y_tstride, a.y_toffset = 1, 0
+    a.B, a.K, a.stride, a.dil, a.pad = B, K, stride, dil, pad
+    if pre is not None:
+        a.pre_a, a.pre_b = ptr(pre[0]), ptr(pre[1])
+    else:
+        a.pre_a, a.pre_b = None, None
+    a.pre_act, a.pre_slope, a.pre_alpha = pre_act, slope, ptr(alpha)
+    if res is not None:
+        assert res.stride(2) == 1 and res.stride(1) == res.shape[2]
+        a.res, a.res_bstride, a.res_len, a.res_shift = ptr(res), res.stride(0), res.shape[2], res_shift
+    else:
+        a.res, a.res_bstride, a.res_len, a.res_shift = None, 0, 0, 0
+    a.out_div, a.accum_mode, a.accum_div, a.out_act = out_div, accum_mode, accum_div, out_act
+    a.stats, a.stats_nparts, a.stats_part_offset = ptr(stats), nparts, 0
+    a.dup_q0_to = -1
+
+
+def conv1d(x, wt, bias=None, *, K, stride=1, dil=1, pad=0, pre=None, pre_act=ACT_NONE, slope=0.0, alpha=None,
+           res=None, res_shift=0, out_div=1.0, accum_mode=0, accum_div=1.0, out_act=ACT_NONE, out=None,
+           want_stats=False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Fused Conv1d (see include/styletts2_b200.h).  wt is the [Cin,K,Cout] layout.
+    Returns (y [B,Cout,Lout], stats [B,Cout,nparts,3] or None)."""
+    x = _cl(x)
+    B, Cin, Lin = x.shape
+    assert wt.shape[0] == Cin and wt.shape[1] == K, (tuple(wt.shape), Cin, K)
+    Cout = wt.shape[2]
+    Lout = (Lin + 2 * pad - dil * (K - 1) - 1) // stride + 1
+    if out is None:
+        out = empty(B, Cout, Lout, device=x.device)
+    assert out.shape == (B, Cout, Lout) and out.stride(2) == 1 and out.stride(1) == Lout
+    nparts = stats_parts(Lout)
+    stats = empty(B, Cout, nparts, 3, device=x.device) if want_stats else None
+    a = ConvArgs()
+    _fill_conv_args(a, x, wt, bias, out, K=K, stride=stride, dil=dil, pad=pad, Lq=Lout, y_len=Lout, pre=pre,
+                    pre_act=pre_act, slope=slope, alpha=alpha, res=res, res_shift=res_shift, out_div=out_div,
+                    accum_mode=accum_mode, accum_div=accum_div, out_act=out_act, stats=stats, nparts=nparts)
+    L.call("st2_conv1d", C.byref(a), stream_ptr())
+    return out, stats
+
+
+def conv_transpose1d(x, wp, bias, *, K, stride, padding, pre_act=ACT_NONE, slope=0.0, alpha=None, res=None,
+                     reflect_left1=False, want_stats=False, out=None):
+    """Polyphase ConvTranspose1d; wp is the [S,Cin,J,Cout] layout; output length Lin*S (+1 if reflect)."""
+    x = _cl(x)
+    B, Cin, Lin = x.shape
+    S = stride
+    assert wp.shape[0] == S and wp.shape[1] == Cin
+    Cout = wp.shape[3]
+    Lout = Lin * S + (1 if reflect_left1 else 0)
+    if out is None:
+        out = empty(B, Cout, Lout, device=x.device)
+    nparts = S * stats_parts(Lin)
+    stats = empty(B, Cout, nparts, 3, device=x.device) if want_stats else None
+    a = ConvArgs()
+    _fill_conv_args(a, x, wp, bias, out, K=1, stride=1, dil=1, pad=0, Lq=Lin, y_len=Lout, pre=None, pre_act=pre_act,
+                    slope=slope, alpha=alpha, res=res, res_shift=0, out_div=1.0, accum_mode=0, accum_div=1.0,
+                    out_act=ACT_NONE, stats=stats, nparts=nparts)
+    L.call("st2_conv_transpose1d", C.byref(a), ptr(wp), K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
+    return out, stats
+
+
+def instance_stats(x) -> torch.Tensor:
+    x = _cl(x)
+    B, Cc, Ln = x.shape
+    st = empty(B, Cc, 1, 3, device=x.device)
+    L.call("st2_instance_stats", ptr(x), x.stride(0), B, Cc, Ln, ptr(st), stream_ptr())
+    return st
+
+
+def adain_coef(stats, gb, eps=1e-5):
+    """stats [B,C,nparts,3]; gb [B,2C] view (row stride free) -> (a,b) each [B,C]."""
+    B, Cc, nparts, _ = stats.shape
+    assert gb.shape == (B, 2 * Cc) and gb.stride(1) == 1
+    a = empty(B, Cc, device=stats.device)
+    b = empty(B, Cc, device=stats.device)
+    L.call("st2_adain_coef", ptr(stats), nparts, ptr(gb), gb.stride(0), B, Cc, eps, ptr(a), ptr(b), stream_ptr())
+    return a, b
+
+
+def adain_lrelu_pool(x, a, b, pool_w, pool_b, slope=0.2):
+    x = _cl(x)
+    B, Cc, Ln = x.shape
+    y = empty(B, Cc, 2 * Ln, device=x.device)
+    L.call("st2_adain_lrelu_pool", ptr(x), x.stride(0), ptr(a), ptr(b), ptr(pool_w), ptr(pool_b), slope, B, Cc, Ln,
+           ptr(y), y.stride(0), stream_ptr())
+    return y
+
+
+def channel_layernorm_lrelu(x, gamma, beta, lengths=None, eps=1e-5, slope=0.2):
+    x = x.contiguous()
+    B, Cc, Ln = x.shape
+    y = torch.empty_like(x)
+    L.call("st2_channel_layernorm_lrelu", ptr(x), ptr(y), ptr(gamma), ptr(beta), eps, slope, ptr(lengths), B, Cc, Ln,
+           stream_ptr())
+    return y
+
+
+# ------------------------------------------------------------------ rows
+def rows_ln(*, B, N, Cw, h_in=None, x=None, xs=1.0, emb=None, add=None, h_out=None, g1=None, b1=None, g2=None, b2=None,
+            gb_bstride=0, ada=False, out1=None, out2=None, eps=1e-5, lengths=None):
+    a = RowsArgs()
+    a.h_in, a.h_in_ld = ptr(h_in), (h_in.stride(-2) if h_in is not None else 0)
+    a.x, a.Cx, a.xs = ptr(x), (x.shape[-1] if x is not None else 0), xs
+    a.emb, a.emb_ld = ptr(emb), (emb.stride(-2) if emb is not None else 0)
+    a.add = ptr(add)
+    a.h_out, a.h_out_ld = ptr(h_out), (h_out.stride(-2) if h_out is not None else 0)
+    a.g1, a.b1, a.g2, a.b2, a.gb_bstride, a.ada = ptr(g1), ptr(b1), ptr(g2), ptr(b2), gb_bstride, 1 if ada else 0
+    a.out1, a.out1_ld = ptr(out1), (out1.stride(-2) if out1 is not None else 0)
+    a.out2, a.out2_ld = ptr(out2), (out2.stride(-2) if out2 is not None else 0)
+    a.B, a.N, a.C, a.eps = B, N, Cw, eps
+    a.lengths = ptr(lengths)
+    L.call("st2_rows_ln", C.byref(a), stream_ptr())
+
+
+def bcast_cols(dst, col0, src, lengths=None):
+    """dst [B,N,ld-view]; dst[:, :, col0:col0+W] = src[b] (masked rows -> 0)"""
+    B, N = dst.shape[0], dst.shape[1]
+    W = src.shape[1]
+    L.call("st2_bcast_cols", ptr(dst), dst.stride(1), col0, ptr(src.contiguous()), B, N, W, ptr(lengths), stream_ptr())
+
+
+def mean_rows(h, B, N):
+    Cw = h.shape[-1]
+    out = empty(B, Cw, device=h.device)
+    L.call("st2_mean_rows", ptr(h), h.stride(-2), B, N, Cw, ptr(out), stream_ptr())
+    return out
+
+
+def _rows_view(t):
+    """(tensor, rows, ld) for a [..., K] tensor whose rows are uniformly strided (else a contiguous copy)."""
+    K = t.shape[-1]
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    if t.dim() == 1:
+        return t, 1, K
+    if t.dim() == 2:
+        return t, t.shape[0], t.stride(0)
+    if t.dim() == 3 and (t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.stride(1)):
+        return t, t.shape[0] * t.shape[1], t.stride(1)
+    t = t.contiguous()
+    return t, t.numel() // K, K
+
+
+def linear(A, W, bias=None, *, act=ACT_NONE, R=None, out=None):
+    """A [..., K] @ W[Nf,K]^T (+bias, act, +R) -> [..., Nf].  Rows may be strided (ld)."""
+    K = A.shape[-1]
+    A2, M, lda = _rows_view(A)
+    Nf = W.shape[0]
+    assert W.shape[1] == K and W.is_contiguous()
+    if out is None:
+        out = empty(*A.shape[:-1], Nf, device=A.device)
+    o2, Mo, ldc = _rows_view(out)
+    assert o2.data_ptr() == out.data_ptr() and Mo == M, "output rows must be uniformly strided"
+    ldr = 0
+    if R is not None:
+        R2, Mr, ldr = _rows_view(R)
+        assert R2.data_ptr() == R.data_ptr() and Mr == M
+    L.call("st2_linear", ptr(A2), 0, lda, 1, M, ptr(W), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
+    return out
+
+
+def linear_strided(x, B, Lr, K, bs, ls, ks, W, bias=None, *, act=ACT_NONE, out=None):
+    """Rows (b,l) of x addressed with explicit strides (conv-layout inputs of LSTM projections)."""
+    Nf = W.shape[0]
+    M = B * Lr
+    if out is None:
+        out = empty(M, Nf, device=x.device)
+    L.call("st2_linear", ptr(x), bs, ls, ks, Lr, ptr(W), ptr(bias), None, 0, ptr(out), out.stride(0), M, Nf, K, act,
+           stream_ptr())
+    return out
+
+
+def attention(q, kv, B, N, H=8, D=64):
+    out = empty(B * N, H * D, device=q.device)
+    L.call("st2_attention", ptr(q), ptr(kv), ptr(out), B, N, H, D, float(D) ** -0.5, stream_ptr())
+    return out
+
+
+def lstm_bidir(gx, whh, out, o_bs, o_ts, o_cs, B, Lr, H, lengths=None):
+    work = empty(6 * B * H, device=gx.device)
+    L.call("st2_lstm_bidir", ptr(gx), ptr(whh), ptr(out), o_bs, o_ts, o_cs, ptr(lengths), B, Lr, H, ptr(work), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------ sampler / glue
+def kdiff_step(x_eval, x_pred, c_skip, c_out, sigma_eval, x_base, dt, eps=None, sigma_up=0.0, x_pred_masked=None,
+               cfg_scale=1.0):
+    out = torch.empty_like(x_base)
+    L.call("st2_kdiff_step", ptr(x_eval), ptr(x_pred), ptr(x_pred_masked), cfg_scale, c_skip, c_out, sigma_eval,
+           ptr(x_base), dt, ptr(eps), sigma_up, ptr(out), x_base.numel(), stream_ptr())
+    return out
+
+
+def scale(x, a):
+    out = torch.empty_like(x)
+    L.call("st2_scale", ptr(x.contiguous()), a, ptr(out), x.numel(), stream_ptr())
+    return out
+
+
+def axpby(x, a, y, b):
+    x, y = x.contiguous(), y.contiguous()
+    out = torch.empty_like(x)
+    L.call("st2_axpby", ptr(x), a, ptr(y), b, ptr(out), x.numel(), stream_ptr())
+    return out
+
+
+def time_embedding(t, w):
+    B, half = t.shape[0], w.shape[0]
+    out = empty(B, 2 * half + 1, device=w.device)
+    L.call("st2_time_embedding", ptr(t.contiguous()), ptr(w), half, B, ptr(out), out.stride(0), stream_ptr())
+    return out
+
+
+def embedding_cl(tokens, table, lengths=None):
+    B, N = tokens.shape
+    Cw = table.shape[1]
+    out = empty(B, Cw, N, device=table.device)
+    L.call("st2_embedding_cl", ptr(tokens.contiguous()), ptr(table), ptr(lengths), B, N, Cw, ptr(out), stream_ptr())
+    return out
+
+
+def durations(logits, last_plus=0):
+    B, N, J = logits.shape
+    pred = torch.empty(B, N, device=logits.device, dtype=torch.int32)
+    durf = empty(B, N, device=logits.device)
+    L.call("st2_durations", ptr(logits.contiguous()), B, N, J, last_plus, ptr(pred), ptr(durf), stream_ptr())
+    return pred, durf
+
+
+def frame_tokens(dur, T, shift_right=False):
+    B, N = dur.shape
+    tok = torch.empty(B, T, device=dur.device, dtype=torch.int32)
+    total = torch.empty(B, device=dur.device, dtype=torch.int32)
+    L.call("st2_frame_tokens", ptr(dur.contiguous()), B, N, T, 1 if shift_right else 0, ptr(tok), ptr(total), stream_ptr())
+    return tok, total
+
+
+def expand_rows(src, tok, out=None):
+    """src [B,N,C] (row stride free) -> [B,T,C]"""
+    B, N, Cw = src.shape
+    T = tok.shape[1]
+    if out is None:
+        out = empty(B, T, Cw, device=src.device)
+    assert src.stride(2) == 1 and src.stride(0) == N * src.stride(1)
+    L.call("st2_expand_rows", ptr(src), src.stride(1), ptr(tok), B, N, T, Cw, ptr(out), out.stride(1), stream_ptr())
+    return out
+
+
+def expand_cl(src, tok, out=None):
+    """src [B,C,N] contiguous -> out [B,C,T] (out may be a channel-prefix view of a wider buffer)"""
+    src = src.contiguous()
+    B, Cw, N = src.shape
+    T = tok.shape[1]
+    if out is None:
+        out = empty(B, Cw, T, device=src.device)
+    L.call("st2_expand_cl", ptr(src), ptr(tok), B, Cw, N, T, ptr(out), out.stride(0), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------ source / stft
+def sine_source(f0, scale_, noise, lin_w, lin_b):
+    """f0 [B,F] -> [B, F*scale]; noise [B,F*scale,9]"""
+    f0 = f0.contiguous()
+    B, F = f0.shape
+    out = empty(B, F * scale_, device=f0.device)
+    work = empty(B * 9 * F, device=f0.device)
+    L.call("st2_sine_source", ptr(f0), B, F, scale_, ptr(noise.contiguous()), ptr(lin_w.contiguous()), ptr(lin_b), ptr(out),
+           ptr(work), stream_ptr())
+    return out
+
+
+def stft20(x):
+    x = x.contiguous()
+    B, Ln = x.shape
+    har = empty(B, 22, Ln // 5 + 1, device=x.device)
+    L.call("st2_stft20", ptr(x), B, Ln, ptr(har), stream_ptr())
+    return har
+
+
+def istft20_expsin(x):
+    x = x.contiguous()
+    B, _, Fr = x.shape
+    wav = empty(B, 5 * (Fr - 1), device=x.device)
+    L.call("st2_istft20_expsin", ptr(x), B, Fr, ptr(wav), stream_ptr())
+    return wav
+
+
+def kdiff_combine(out, out_masked, scale_):
+    """classifier-free guidance: out_masked + (out - out_masked) * scale (modules.py:420-423)"""
+    d = axpby(out, 1.0, out_masked, -1.0)
+    return axpby(out_masked, 1.0, d, scale_)
