@@ -41,9 +41,11 @@ class Synthesizer:
     @torch.no_grad()
     def synthesize(self, tokens, input_lengths, bert_dur, noise, *, diffusion_steps=5, embedding_scale=1.0, ref_s=None,
                    alpha=0.3, beta=0.7, rng: Optional[Dict] = None, forced_durations=None, pin_frames_per_token=None,
-                   return_all=False):
+                   return_all=False, decoder_events=None):
         """tokens [B,N] i64, input_lengths [B], bert_dur [B,N,768], noise [B,1,256] (device tensors).
-        rng (parity mode): 'step_noises' list of [B,1,256], 'sine_noise' [B,L,9], 'har' [B,22,F].
+        rng (parity mode): 'step_noises' list of [B,1,256], 'sine_noise' [B,L,9], 'har' [B,22,F],
+        'F0' / 'N' [B,2T] (teacher-forced prosody curves: the harmonic source integrates F0 into a phase
+        of 1e4..1e6 rad, so waveform comparisons inject the reference's curves after checking ours).
         forced_durations [B,N] int: teacher-forced durations (after the duration kernel has run).
         pin_frames_per_token: throughput mode of SURVEY section 8d (durations pinned so that T = N*k)."""
         m = self.model
@@ -82,7 +84,15 @@ class Synthesizer:
         en_rows = ops.expand_rows(d, tok)                                         # [B,T,640]
         asr = ops.expand_cl(t_en, tok)                                            # [B,512,T]
         F0, Ncurve = m.predictor.F0Ntrain(en_rows.transpose(-1, -2), s)
-        wav = m.decoder(asr, F0, Ncurve, ref, sine_noise=rng.get("sine_noise"), har=rng.get("har"))
+        F0_used = rng["F0"] if "F0" in rng else F0
+        N_used = rng["N"] if "N" in rng else Ncurve
+        if decoder_events is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        wav = m.decoder(asr, F0_used, N_used, ref, sine_noise=rng.get("sine_noise"), har=rng.get("har"))
+        if decoder_events is not None:
+            ev1.record()
+            decoder_events.append((ev0, ev1))
         out = dict(wav=wav, pred_dur=pred_dur, T=T)
         if return_all:
             out.update(t_en=t_en, d_en=d_en_rows.transpose(-1, -2), s_pred=s_pred, s=s, ref=ref, d=d, logits=logits,

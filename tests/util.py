@@ -62,3 +62,11 @@ def gpu_model(model_name):
         load_keyed_weights(m)
         _MODELS[model_name] = m
     return _MODELS[model_name]
+
+
+def record(name, **vals):
+    """Append measured parity figures to gpurun_out/parity_report.jsonl (kept as evidence under profiles/)."""
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps(dict(test=name, **{k: (float(v) if not isinstance(v, (int, str, bool)) else v) for k, v in vals.items()})) + "\n")
