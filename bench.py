@@ -165,6 +165,11 @@ def run_ours(args):
     launches = lib.launch_count() - n0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     dec_ms = sum(a.elapsed_time(b) for a, b in dec_ev) / max(1, len(dec_ev))
+    if args.skip_e2e:
+        if rank == 0:
+            clocks.stop()
+            print(json.dumps({"profile_only": True, "ms_per_step": ms_total / args.steps, "decoder_ms": dec_ms, "gpu_launches": launches}))
+        return
     # ---- end to end through the public API with HOST buffers (`e2e`)
     def e2e_step():
         ins = [t.to(dev, non_blocking=True) for t in host]
@@ -267,6 +272,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident loop, no JSON contract line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

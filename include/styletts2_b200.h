@@ -89,6 +89,21 @@ int st2_conv1d(const st2_conv_args* a, void* stream);
 /* number of stats partials st2_conv1d writes for Lq outputs */
 int st2_conv_stats_parts(int Lq);
 
+/* Tensor-core path of the same fused Conv1d (stride 1): tcgen05 implicit GEMM with TMEM accumulators,
+ * bf16 hi/lo split operands (hi*hi + hi*lo + lo*hi, fp32 accumulate), weights streamed by 1-D TMA bulk
+ * copies.  `wtc` is the st2_conv_tc_weight_layout buffer (st2_conv_tc_weight_bytes bytes) built from the
+ * folded fp32 weight [Cout,Cin,K].  a->w is ignored; every other field means what it means for st2_conv1d.
+ * max_ctas > 0 caps the persistent grid (testing).  Same call sites as st2_conv1d. */
+long long st2_conv_tc_weight_bytes(int Cout, int Cin, int K);
+int st2_conv_tc_weight_layout(const float* w, void* out, int Cout, int Cin, int K, void* stream);
+int st2_conv_tc_supported(int Cin, int Cout, int K, int stride, int dil);
+int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int max_ctas, void* stream);
+/* Polyphase ConvTranspose1d on the same tensor-core kernel (one launch per phase); wtc from
+ * st2_convT_tc_weight_layout (st2_convT_tc_weight_bytes bytes).  Arguments as st2_conv_transpose1d. */
+long long st2_convT_tc_weight_bytes(int Cin, int Cout, int K, int S);
+int st2_convT_tc_weight_layout(const float* w, void* out, int Cin, int Cout, int K, int S, int P, void* stream);
+int st2_conv_transpose1d_tc(const st2_conv_args* a, const void* wtc, int K, int S, int P, int reflect_left1, void* stream);
+
 /* ConvTranspose1d (stride S, K taps, padding P; output length Lin*S) as S polyphase
  * stride-1 convolutions through the same fused kernel; `a` describes the x / y / prologue /
  * epilogue exactly as for st2_conv1d with K,stride,dil,pad,Lq,y_tstride,y_toffset,w ignored;

@@ -1,0 +1,584 @@
+// Tensor-core (tcgen05 / TMEM) implicit-GEMM Conv1d for the vocoder's AdaIN ResBlocks -- sm_100a.
+//
+//   D[co (M=128), t (N=256)] = sum_{tap} sum_{ci} W_tap[co, ci] * z[ci, t + tap*dil - pad],   z = snake/lrelu(a*x+b)
+//
+// Precision recipe (decided with the CPU oracle, DESIGN.md "precision"): fp32 operands are split into
+// bf16 hi + bf16 lo and every product is evaluated as hi*hi + hi*lo + lo*hi on the 5th-gen tensor
+// cores with fp32 accumulation in TMEM (error ~2^-16 relative per product, 2.8e-5 max-abs on the
+// waveform vs 1.3e-3 for single-pass TF32 and 1.2e-2 for plain bf16).
+//
+// Mapping:
+//  * A operand = weights  [128 co x 16 ci] bf16, K-major, no-swizzle "interleave" layout (8-row x 16-byte core
+//    matrices, rows contiguous at 16 B pitch).  Pre-arranged in HBM so that one pipeline stage (tap, 32 ci,
+//    hi+lo) is ONE contiguous 16 KB block moved by a single 1-D TMA bulk copy (cp.async.bulk) that signals
+//    an mbarrier.
+//  * B operand = activations [256 t x 16 ci] bf16, K-major, same interleave layout: for each group of 8
+//    input channels the frame window is a column of 16-byte rows, so a conv tap is just a descriptor start
+//    address shifted by tap*dil rows (16 B granularity) -- the window is staged ONCE per 32-channel block
+//    (AdaIN affine + Snake/LeakyReLU + hi/lo split fused into the staging) and re-used by all K taps.
+//  * D accumulators live in TMEM (2 x 256 columns, double buffered so the epilogue of tile i overlaps the
+//    MMAs of tile i+1); the epilogue reads them with tcgen05.ld, transposes 32x32 blocks through shared
+//    memory for coalesced row stores and fuses bias, residual, MRF accumulation and the InstanceNorm
+//    partial statistics (count, mean, M2) exactly like the SIMT kernel.
+//  * Warp roles: warp 0 = TMEM alloc + single-thread MMA issue, warp 1 = weight TMA producer,
+//    warps 2-9 = activation stagers, warps 10-13 = epilogue.  Persistent CTAs (one per SM) loop over tiles.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace st2 {
+extern long long g_launches;
+
+namespace tc {
+
+constexpr int TN = 256;
+constexpr int TM = 128;
+constexpr int CB = 32;
+constexpr int W_STAGES = 4;
+constexpr int W_STAGE_BYTES = 2 * 4 * TM * 16;  // (hi|lo) x 4 k-chunks x 128 co x 16 B
+constexpr int RW_MAX = 312;                     // TN + (K-1)*dil rounded up to 8, max
+constexpr int ACT_HALF_BYTES = 4 * RW_MAX * 16; // one of hi / lo for one 32-channel block
+constexpr int ACT_BUF_BYTES = 2 * ACT_HALF_BYTES;
+constexpr int CIN_PAD_MAX = 1120;
+constexpr int NUM_STAGERS = 256;
+constexpr int NUM_EPI = 128;
+constexpr int THREADS = 64 + NUM_STAGERS + NUM_EPI;  // 448
+
+constexpr int SM_W = 0;
+constexpr int SM_ACT = SM_W + W_STAGES * W_STAGE_BYTES;
+constexpr int SM_COEF = SM_ACT + 2 * ACT_BUF_BYTES;
+constexpr int SM_EPI = SM_COEF + 3 * CIN_PAD_MAX * 4;
+constexpr int SM_BAR = SM_EPI + 4 * 32 * 33 * 4;
+constexpr int SM_TOTAL = SM_BAR + 256;
+
+// barrier slots (8 B each) inside SM_BAR
+constexpr int B_WFULL = 0, B_WEMPTY = 4, B_AFULL = 8, B_AEMPTY = 10, B_TFULL = 12, B_TEMPTY = 14, B_COUNT = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, SWIZZLE_NONE (interleave) shared-memory matrix descriptor: start address, LBO = byte distance between the
+// two 8-element K chunks of one MMA, SBO = byte distance between 8-row groups (128 B: rows are contiguous).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset = 0, lbo_mode = 0, layout_type = 0 (no swizzle)
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256.
+__device__ __forceinline__ uint32_t make_idesc() {
+  uint32_t d = 0;
+  d |= 1u << 4;                 // c_format = F32
+  d |= 1u << 7;                 // a_format = BF16
+  d |= 1u << 10;                // b_format = BF16
+  d |= (uint32_t)(TN >> 3) << 17;  // n_dim
+  d |= (uint32_t)(TM >> 4) << 24;  // m_dim
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TileCoord {
+  int b, cob, tq;
+};
+__device__ __forceinline__ TileCoord tile_coord(int tile, int n_tq, int n_cob) {
+  TileCoord c;
+  c.tq = tile % n_tq;
+  const int r = tile / n_tq;
+  c.cob = r % n_cob;
+  c.b = r / n_cob;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int ncb, const int RW, const int ntiles,
+                 const int n_tq, const int n_cob) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + SM_BAR;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * B_COUNT);
+
+  if (tid == 0) {
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(B_AFULL + i), NUM_STAGERS);
+      mbar_init(BAR(B_AEMPTY + i), 1);
+      mbar_init(BAR(B_TFULL + i), 1);
+      mbar_init(BAR(B_TEMPTY + i), NUM_EPI);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int K = a.K;
+
+  if (warp == 0) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc();
+      const uint32_t lbo_a = TM * 16, lbo_b = (uint32_t)RW * 16;
+      int ws = 0, wph = 0, as = 0, aph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(BAR(B_TEMPTY + buf), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * TN;
+        uint32_t first = 1;
+        for (int cb = 0; cb < ncb; ++cb) {
+          mbar_wait(BAR(B_AFULL + as), aph);
+          tc_fence_after();
+          const uint32_t act_hi = sbase + SM_ACT + as * ACT_BUF_BYTES;
+          const uint32_t act_lo = act_hi + ACT_HALF_BYTES;
+          for (int tap = 0; tap < K; ++tap) {
+            mbar_wait(BAR(B_WFULL + ws), wph);
+            tc_fence_after();
+            const uint32_t w_hi = sbase + SM_W + ws * W_STAGE_BYTES;
+            const uint32_t w_lo = w_hi + W_STAGE_BYTES / 2;
+            const uint32_t row_off = (uint32_t)(tap * a.dil) * 16;
+#pragma unroll
+            for (int k16 = 0; k16 < 2; ++k16) {
+              const uint32_t aoff = (uint32_t)(2 * k16) * lbo_a;
+              const uint32_t boff = (uint32_t)(2 * k16) * lbo_b + row_off;
+              const uint64_t da_hi = make_desc(w_hi + aoff, lbo_a, 128), da_lo = make_desc(w_lo + aoff, lbo_a, 128);
+              const uint64_t db_hi = make_desc(act_hi + boff, lbo_b, 128), db_lo = make_desc(act_lo + boff, lbo_b, 128);
+              tc_mma(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
+              first = 0;
+              tc_mma(d_tmem, da_hi, db_lo, idesc, 1u);
+              tc_mma(d_tmem, da_lo, db_hi, idesc, 1u);
+            }
+            tc_commit(BAR(B_WEMPTY + ws));
+            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+          }
+          tc_commit(BAR(B_AEMPTY + as));
+          if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        tc_commit(BAR(B_TFULL + buf));
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ weight producer (1-D TMA bulk copies)
+    if (lane == 0) {
+      int ws = 0, wph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
+        for (int cb = 0; cb < ncb; ++cb) {
+          for (int tap = 0; tap < K; ++tap) {
+            mbar_wait(BAR(B_WEMPTY + ws), wph ^ 1);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(wtc) +
+                                 ((size_t)((tap * n_cob + tc_.cob) * ncb + cb)) * W_STAGE_BYTES;
+            mbar_expect_tx(BAR(B_WFULL + ws), W_STAGE_BYTES);
+            bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, W_STAGE_BYTES, BAR(B_WFULL + ws));
+            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp < 2 + NUM_STAGERS / 32) {
+    // ================================================================ activation stagers
+    const int st = tid - 64;  // 0..255
+    float* coef = reinterpret_cast<float*>(smem + SM_COEF);
+    const int cin_pad = ncb * CB;
+    int as = 0, aph = 0;
+    int last_b = -1;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
+      if (tc_.b != last_b) {
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));  // everybody done reading the old table
+        for (int c = st; c < cin_pad; c += NUM_STAGERS) {
+          float pa = 1.f, pb = 0.f, al = 1.f;
+          if (c < a.Cin) {
+            if (a.pre_a) { pa = a.pre_a[tc_.b * a.Cin + c]; pb = a.pre_b[tc_.b * a.Cin + c]; }
+            if (a.pre_act == ST2_ACT_SNAKE) al = a.pre_alpha[c];
+          }
+          coef[c] = pa; coef[CIN_PAD_MAX + c] = pb; coef[2 * CIN_PAD_MAX + c] = al;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));
+        last_b = tc_.b;
+      }
+      const float* xb = a.x + (long long)tc_.b * a.x_bstride;
+      const int g0 = tc_.tq * TN - a.pad;  // global time of window row 0
+      for (int cb = 0; cb < ncb; ++cb) {
+        mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
+        uint8_t* hi = smem + SM_ACT + as * ACT_BUF_BYTES;
+        uint8_t* lo = hi + ACT_HALF_BYTES;
+        for (int r = st; r < RW; r += NUM_STAGERS) {
+          const int g = g0 + r;
+          const bool inb = (g >= 0) && (g < a.Lin);
+          const int cbase = cb * CB;
+          float xv[CB];
+          // all 32 channel loads of this frame are issued before any is consumed (memory-level parallelism)
+#pragma unroll
+          for (int q = 0; q < CB; ++q) {
+            const int c = cbase + q;
+            xv[q] = (inb && c < a.Cin) ? __ldg(xb + (long long)c * a.Lin + g) : 0.f;
+          }
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = cbase + kc * 8 + j;
+              float z = 0.f;
+              if (inb && c < a.Cin) {
+                z = fmaf(xv[kc * 8 + j], coef[c], coef[CIN_PAD_MAX + c]);
+                if (a.pre_act == ST2_ACT_SNAKE) {
+                  const float al = coef[2 * CIN_PAD_MAX + c];
+                  const float sn = __sinf(al * z);
+                  z = z + __fdividef(1.0f, al) * (sn * sn);
+                } else if (a.pre_act == ST2_ACT_LRELU) {
+                  z = z > 0.f ? z : z * a.pre_slope;
+                }
+              }
+              v[j] = z;
+            }
+            uint4 h4, l4;
+            float h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+            h4.x = pack_bf16(h[0], h[1]); h4.y = pack_bf16(h[2], h[3]); h4.z = pack_bf16(h[4], h[5]); h4.w = pack_bf16(h[6], h[7]);
+            l4.x = pack_bf16(v[0] - h[0], v[1] - h[1]); l4.y = pack_bf16(v[2] - h[2], v[3] - h[3]);
+            l4.z = pack_bf16(v[4] - h[4], v[5] - h[5]); l4.w = pack_bf16(v[6] - h[6], v[7] - h[7]);
+            *reinterpret_cast<uint4*>(hi + (size_t)(kc * RW + r) * 16) = h4;
+            *reinterpret_cast<uint4*>(lo + (size_t)(kc * RW + r) * 16) = l4;
+          }
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(BAR(B_AFULL + as));
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================ epilogue
+    const int ew = warp & 3;  // TMEM lane quarter this warp may access
+    float* T = reinterpret_cast<float*>(smem + SM_EPI) + ew * 32 * 33;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
+      const int buf = it & 1;
+      mbar_wait(BAR(B_TFULL + buf), (it >> 1) & 1);
+      tc_fence_after();
+      const int co_base = tc_.cob * TM + ew * 32;
+      const int t0 = tc_.tq * TN;
+      const int ncols = min(TN, a.Lq - t0);
+      float* yb = a.y + (long long)tc_.b * a.y_bstride;
+      // running (count, mean, M2) of row (co_base + lane)
+      float s_n = 0.f, s_mean = 0.f, s_m2 = 0.f;
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + c0), v);
+        if (c0 >= ncols) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int t = t0 + c0 + lane;
+        const bool tv = (c0 + lane) < ncols;
+        const int oidx = t * a.y_tstride + a.y_toffset;
+        const int rmax = min(32, a.Cout - co_base);  // warp-uniform
+        for (int r0 = 0; r0 < rmax; r0 += 8) {
+          float rv[8], yo[8];
+          // residual / accumulator loads of 8 rows are in flight together
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int co = co_base + r0 + i;
+            const bool ok = tv && (r0 + i) < rmax;
+            rv[i] = (ok && a.res) ? __ldg(a.res + (long long)tc_.b * a.res_bstride + (long long)co * a.res_len + (oidx >> a.res_shift)) : 0.f;
+            yo[i] = (ok && a.accum_mode) ? yb[(long long)co * a.y_len + oidx] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + i;
+            if (r >= rmax) break;
+            const int co = co_base + r;
+            float val = 0.f;
+            if (tv) {
+              val = T[r * 33 + lane] + (a.bias ? a.bias[co] : 0.f) + rv[i];
+              if (a.out_div != 1.0f) val = __fdiv_rn(val, a.out_div);
+              if (a.accum_mode == 1) val = yo[i] + val;
+              else if (a.accum_mode == 2) val = __fdiv_rn(yo[i] + val, a.accum_div);
+              if (a.out_act == ST2_ACT_TANH) val = tanhf(val);
+              yb[(long long)co * a.y_len + oidx] = val;
+            }
+            if (a.stats) T[r * 33 + lane] = val;
+          }
+        }
+        // ReflectionPad1d((1,0)) duplicate of the q==0 column (istftnet.py:365-366): value differs by its residual
+        const bool dup_here = (a.dup_q0_to >= 0) && (t0 == 0) && (c0 == 0);
+        float dupv = 0.f;
+        if (dup_here) {
+          const int co = co_base + lane;  // here each lane owns one row; column 0 of the accumulator block
+          if (co < a.Cout) {
+            float val = v[0] + (a.bias ? a.bias[co] : 0.f);
+            if (a.res) val += a.res[(long long)tc_.b * a.res_bstride + (long long)co * a.res_len + (a.dup_q0_to >> a.res_shift)];
+            if (a.out_div != 1.0f) val = __fdiv_rn(val, a.out_div);
+            float* p = yb + (long long)co * a.y_len + a.dup_q0_to;
+            if (a.accum_mode == 1) val = *p + val;
+            else if (a.accum_mode == 2) val = __fdiv_rn(*p + val, a.accum_div);
+            if (a.out_act == ST2_ACT_TANH) val = tanhf(val);
+            *p = val;
+            dupv = val;
+          }
+        }
+        if (a.stats) {
+          __syncwarp();
+          const int nv = min(32, ncols - c0);
+          float cs = 0.f;
+          for (int j = 0; j < nv; ++j) cs += T[lane * 33 + j];
+          const float cmean = cs / (float)nv;
+          float cm2 = 0.f;
+          for (int j = 0; j < nv; ++j) {
+            const float d = T[lane * 33 + j] - cmean;
+            cm2 = fmaf(d, d, cm2);
+          }
+          // Chan merge
+          const float nn = s_n + (float)nv;
+          const float delta = cmean - s_mean;
+          s_mean += delta * ((float)nv / nn);
+          s_m2 += cm2 + delta * delta * (s_n * (float)nv / nn);
+          s_n = nn;
+          if (dup_here) {  // one extra sample for this row
+            const float n2 = s_n + 1.0f;
+            const float d2 = dupv - s_mean;
+            s_mean += d2 / n2;
+            s_m2 += d2 * d2 * (s_n / n2);
+            s_n = n2;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(B_TEMPTY + buf));
+      if (a.stats) {
+        const int co = co_base + lane;
+        if (co < a.Cout) {
+          float* sp = a.stats + (((long long)tc_.b * a.Cout + co) * a.stats_nparts + a.stats_part_offset + tc_.tq) * 3;
+          sp[0] = s_n; sp[1] = s_mean; sp[2] = s_m2;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// fp32 [Cout,Cin,K] -> bf16 hi/lo stage blocks [K][n_cob][ncb][2][4][128][8]
+__global__ void conv_tc_weight_layout_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int K,
+                                             int n_cob, int ncb) {
+  const long long total = (long long)K * n_cob * ncb * 2 * 4 * TM * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int j = (int)(r % 8); r /= 8;
+    const int col = (int)(r % TM); r /= TM;
+    const int kc = (int)(r % 4); r /= 4;
+    const int hl = (int)(r % 2); r /= 2;
+    const int cb = (int)(r % ncb); r /= ncb;
+    const int cob = (int)(r % n_cob); r /= n_cob;
+    const int tap = (int)r;
+    const int co = cob * TM + col, ci = cb * CB + kc * 8 + j;
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * K + tap];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = hl == 0 ? h : __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// ConvTranspose1d weight [Cin,Cout,K] -> S per-phase tensor-core blocks (phase r = J-tap stride-1 conv, see conv.cu)
+__global__ void convT_tc_weight_layout_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Cout, int K,
+                                              int S, int P, int J, int n_cob, int ncb) {
+  const long long per_phase = (long long)J * n_cob * ncb * 2 * 4 * TM * 8;
+  const long long total = per_phase * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ph = (int)(i / per_phase);
+    long long r = i % per_phase;
+    const int j = (int)(r % 8); r /= 8;
+    const int col = (int)(r % TM); r /= TM;
+    const int kc = (int)(r % 4); r /= 4;
+    const int hl = (int)(r % 2); r /= 2;
+    const int cb = (int)(r % ncb); r /= ncb;
+    const int cob = (int)(r % n_cob); r /= n_cob;
+    const int kp = (int)r;  // tap of the phase conv
+    const int co = cob * TM + col, ci = cb * CB + kc * 8 + j;
+    const int kk = (J - 1 - kp) * S + ((ph + P) % S);
+    float v = 0.f;
+    if (co < Cout && ci < Cin && kk < K) v = w[((long long)ci * Cout + co) * K + kk];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = hl == 0 ? h : __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+static int launch_tc(const st2_conv_args& a, const void* wtc, int max_ctas, cudaStream_t st) {
+  const int n_tq = cdiv(a.Lq, TN), n_cob = cdiv(a.Cout, TM), ncb = cdiv(a.Cin, CB);
+  const int rw = (TN + (a.K - 1) * a.dil + 7) & ~7;
+  const int ntiles = a.B * n_cob * n_tq;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+  }
+  int grid = ntiles < num_sms ? ntiles : num_sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  conv1d_tc_kernel<<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
+  ++g_launches;
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace st2
+
+using namespace st2;
+
+extern "C" {
+
+long long st2_conv_tc_weight_bytes(int Cout, int Cin, int K) {
+  const int n_cob = cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB);
+  return (long long)K * n_cob * ncb * tc::W_STAGE_BYTES;
+}
+
+int st2_conv_tc_weight_layout(const float* w, void* out, int Cout, int Cin, int K, void* stream) {
+  ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0, "st2_conv_tc_weight_layout", "bad args");
+  const int n_cob = cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB);
+  tc::conv_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out, Cout, Cin, K, n_cob, ncb);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_conv_tc_weight_layout");
+  return 0;
+}
+
+int st2_conv_tc_supported(int Cin, int Cout, int K, int stride, int dil) {
+  const int rw = (tc::TN + (K - 1) * dil + 7) & ~7;
+  return stride == 1 && rw <= tc::RW_MAX && cdiv(Cin, tc::CB) * tc::CB <= tc::CIN_PAD_MAX;
+}
+
+int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int max_ctas, void* stream) {
+  ST2_REQUIRE(a && a->x && wtc && a->y, "st2_conv1d_tc", "null pointer");
+  ST2_REQUIRE(st2_conv_tc_supported(a->Cin, a->Cout, a->K, a->stride, a->dil), "st2_conv1d_tc", "unsupported shape");
+  ST2_REQUIRE(a->pre_act != ST2_ACT_SNAKE || a->pre_alpha, "st2_conv1d_tc", "snake prologue needs alpha");
+  const int n_tq = cdiv(a->Lq, tc::TN);
+  ST2_REQUIRE(!a->stats || a->stats_nparts >= a->stats_part_offset + n_tq, "st2_conv1d_tc", "stats buffer too small");
+  tc::launch_tc(*a, wtc, max_ctas, (cudaStream_t)stream);
+  ST2_CHECK_LAUNCH("st2_conv1d_tc");
+  return 0;
+}
+
+long long st2_convT_tc_weight_bytes(int Cin, int Cout, int K, int S) {
+  const int J = (K + S - 1) / S;
+  return (long long)S * st2_conv_tc_weight_bytes(Cout, Cin, J);
+}
+
+int st2_convT_tc_weight_layout(const float* w, void* out, int Cin, int Cout, int K, int S, int P, void* stream) {
+  ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0 && S > 0, "st2_convT_tc_weight_layout", "bad args");
+  const int J = (K + S - 1) / S;
+  const int n_cob = cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB);
+  tc::convT_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out, Cin, Cout, K, S, P, J, n_cob, ncb);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_convT_tc_weight_layout");
+  return 0;
+}
+
+int st2_conv_transpose1d_tc(const st2_conv_args* a0, const void* wtc, int K, int S, int P, int reflect_left1, void* stream) {
+  ST2_REQUIRE(a0 && a0->x && wtc && a0->y, "st2_conv_transpose1d_tc", "null pointer");
+  ST2_REQUIRE(K > 0 && S > 0 && P >= 0, "st2_conv_transpose1d_tc", "bad shape");
+  const int J = (K + S - 1) / S;
+  ST2_REQUIRE(st2_conv_tc_supported(a0->Cin, a0->Cout, J, 1, 1), "st2_conv_transpose1d_tc", "unsupported shape");
+  const int parts = cdiv(a0->Lin, tc::TN);
+  ST2_REQUIRE(!a0->stats || a0->stats_nparts >= S * parts, "st2_conv_transpose1d_tc", "stats buffer too small");
+  const long long phase_bytes = st2_conv_tc_weight_bytes(a0->Cout, a0->Cin, J);
+  for (int r = 0; r < S; ++r) {
+    st2_conv_args a = *a0;
+    const int cr = (r + P) / S;
+    a.K = J;
+    a.stride = 1;
+    a.dil = 1;
+    a.pad = (J - 1) - cr;
+    a.Lq = a0->Lin;
+    a.y_tstride = S;
+    a.y_toffset = r + (reflect_left1 ? 1 : 0);
+    a.y_len = a0->Lin * S + (reflect_left1 ? 1 : 0);
+    a.stats_part_offset = r * parts;
+    a.dup_q0_to = (reflect_left1 && r == 1) ? 0 : -1;
+    tc::launch_tc(a, (const uint8_t*)wtc + (size_t)r * phase_bytes, 0, (cudaStream_t)stream);
+  }
+  ST2_CHECK_LAUNCH("st2_conv_transpose1d_tc");
+  return 0;
+}
+
+}  // extern "C"

@@ -55,6 +55,13 @@ SIGNATURES = {
     "st2_convT_weight_layout": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "st2_conv1d": [C.POINTER(ConvArgs), _vp],
     "st2_conv_stats_parts": [_i],
+    "st2_conv_tc_weight_bytes": [_i, _i, _i],
+    "st2_conv_tc_weight_layout": [_vp, _vp, _i, _i, _i, _vp],
+    "st2_conv_tc_supported": [_i, _i, _i, _i, _i],
+    "st2_conv1d_tc": [C.POINTER(ConvArgs), _vp, _i, _vp],
+    "st2_convT_tc_weight_bytes": [_i, _i, _i, _i],
+    "st2_convT_tc_weight_layout": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "st2_conv_transpose1d_tc": [C.POINTER(ConvArgs), _vp, _i, _i, _i, _i, _vp],
     "st2_conv_transpose1d": [C.POINTER(ConvArgs), _vp, _i, _i, _i, _i, _vp],
     "st2_instance_stats": [_vp, _ll, _i, _i, _i, _vp, _vp],
     "st2_adain_coef": [_vp, _i, _vp, _ll, _i, _i, _f, _vp, _vp, _vp],
@@ -79,7 +86,8 @@ SIGNATURES = {
     "st2_stft20": [_vp, _i, _i, _vp, _vp],
     "st2_istft20_expsin": [_vp, _i, _i, _vp, _vp],
 }
-_RESTYPES = {"st2_last_error": C.c_char_p, "st2_launch_count": C.c_longlong}
+_RESTYPES = {"st2_last_error": C.c_char_p, "st2_launch_count": C.c_longlong, "st2_conv_tc_weight_bytes": C.c_longlong,
+             "st2_convT_tc_weight_bytes": C.c_longlong}
 
 _lib = None
 

@@ -54,7 +54,7 @@ class WNConv1d(_Cached):
 
     def _prepare(self):
         w = ops.fold_weight_norm(self.weight_v, self.weight_g)
-        return ops.conv_weight_layout(w), w
+        return ops.conv_weight_layout(w), w, _maybe_wtc(w, self.stride, self.dilation)
 
     def wt(self):
         return self.prepared()[0]
@@ -62,9 +62,21 @@ class WNConv1d(_Cached):
     def folded(self):
         return self.prepared()[1]
 
+    def wtc(self):
+        return self.prepared()[2]
+
     def forward(self, x, **kw):
-        y, _ = ops.conv1d(x, self.wt(), self.bias, K=self.k, stride=self.stride, dil=self.dilation, pad=self.padding, **kw)
+        y, _ = ops.conv1d(x, self.wt(), self.bias, K=self.k, stride=self.stride, dil=self.dilation, pad=self.padding,
+                          wtc=self.wtc(), **kw)
         return y
+
+
+def _maybe_wtc(w, stride, dilation):
+    """bf16 hi/lo tensor-core weight blocks when the tcgen05 conv supports the shape and it is worth it."""
+    co, ci, k = w.shape
+    if stride == 1 and co >= 16 and ci >= 16 and ops.conv_tc_supported(ci, co, k, stride, dilation):
+        return ops.conv_tc_weight_layout(w)
+    return None
 
 
 class Conv1d(_Cached):
@@ -77,13 +89,16 @@ class Conv1d(_Cached):
         self.bias = nn.Parameter(torch.zeros(cout))
 
     def _prepare(self):
-        return ops.conv_weight_layout(self.weight)
+        return ops.conv_weight_layout(self.weight), _maybe_wtc(self.weight.detach(), self.stride, 1)
 
     def wt(self):
-        return self.prepared()
+        return self.prepared()[0]
+
+    def wtc(self):
+        return self.prepared()[1]
 
     def forward(self, x, **kw):
-        y, _ = ops.conv1d(x, self.wt(), self.bias, K=self.k, stride=self.stride, pad=self.padding, **kw)
+        y, _ = ops.conv1d(x, self.wt(), self.bias, K=self.k, stride=self.stride, pad=self.padding, wtc=self.wtc(), **kw)
         return y
 
 
@@ -101,14 +116,21 @@ class WNConvTranspose1d(_Cached):
     def _prepare(self):
         w = ops.fold_weight_norm(self.weight_v, self.weight_g)
         if self.groups == 1:
-            return ops.convT_weight_layout(w, self.stride, self.padding), w
-        return None, w.contiguous()
+            J = (self.k + self.stride - 1) // self.stride
+            wtc = None
+            if self.cin >= 16 and self.cout >= 16 and ops.conv_tc_supported(self.cin, self.cout, J, 1, 1):
+                wtc = ops.convT_tc_weight_layout(w, self.stride, self.padding)
+            return ops.convT_weight_layout(w, self.stride, self.padding), w, wtc
+        return None, w.contiguous(), None
 
     def wp(self):
         return self.prepared()[0]
 
     def folded(self):
         return self.prepared()[1]
+
+    def wtc(self):
+        return self.prepared()[2]
 
 
 class Linear(nn.Linear):
@@ -278,17 +300,17 @@ class AdainResBlk1d(nn.Module):
         up = self.has_upsample
         if up:
             r = ops.adain_lrelu_pool(x, a1, b1, self.pool.folded().view(-1, 3), self.pool.bias, 0.2)
-            h, hst = ops.conv1d(r, self.conv1.wt(), self.conv1.bias, K=3, pad=1, want_stats=True)
+            h, hst = ops.conv1d(r, self.conv1.wt(), self.conv1.bias, K=3, pad=1, want_stats=True, wtc=self.conv1.wtc())
         else:
             h, hst = ops.conv1d(x, self.conv1.wt(), self.conv1.bias, K=3, pad=1, pre=(a1, b1), pre_act=ACT_LRELU, slope=0.2,
-                                want_stats=True)
+                                want_stats=True, wtc=self.conv1.wtc())
         a2, b2 = self.norm2.coef(hst, fcs)
         if self.learned_sc:
-            sc, _ = ops.conv1d(x, self.conv1x1.wt(), None, K=1)
+            sc, _ = ops.conv1d(x, self.conv1x1.wt(), None, K=1, wtc=self.conv1x1.wtc())
         else:
             sc = x
         y, _ = ops.conv1d(h, self.conv2.wt(), self.conv2.bias, K=3, pad=1, pre=(a2, b2), pre_act=ACT_LRELU, slope=0.2, res=sc,
-                          res_shift=1 if up else 0, out_div=math.sqrt(2), out=out)
+                          res_shift=1 if up else 0, out_div=math.sqrt(2), out=out, wtc=self.conv2.wtc())
         return y
 
     def forward(self, x, s):
@@ -335,7 +357,7 @@ class TextEncoder(nn.Module):
         h = ops.embedding_cl(x.to(dev), self.embedding.weight, lens)
         for blk in self.cnn:
             conv, ln = blk[0], blk[1]
-            y, _ = ops.conv1d(h, conv.wt(), conv.bias, K=conv.k, pad=conv.padding)
+            y, _ = ops.conv1d(h, conv.wt(), conv.bias, K=conv.k, pad=conv.padding, wtc=conv.wtc())
             h = ops.channel_layernorm_lrelu(y, ln.gamma, ln.beta, lens, ln.eps, 0.2)
         C = self.channels
         out = torch.zeros(B, C, N, device=dev)
@@ -463,13 +485,13 @@ class AdaINResBlock1(nn.Module):
             c1, c2 = self.convs1[j], self.convs2[j]
             a1, b1 = self.adain1[j].coef(st, fcs)
             h, hst = ops.conv1d(x, c1.wt(), c1.bias, K=k, dil=c1.dilation, pad=c1.padding, pre=(a1, b1), pre_act=ACT_SNAKE,
-                                alpha=self.alpha1[j], want_stats=True)
+                                alpha=self.alpha1[j], want_stats=True, wtc=c1.wtc())
             a2, b2 = self.adain2[j].coef(hst, fcs)
             last = j == n - 1
             x, st = ops.conv1d(h, c2.wt(), c2.bias, K=k, dil=1, pad=c2.padding, pre=(a2, b2), pre_act=ACT_SNAKE,
                                alpha=self.alpha2[j], res=x, want_stats=(not last) or final_stats,
                                out=out if last else None, accum_mode=accum_mode if last else 0,
-                               accum_div=accum_div if last else 1.0)
+                               accum_div=accum_div if last else 1.0, wtc=c2.wtc())
         return x, st
 
     def forward(self, x, s):
@@ -546,12 +568,13 @@ class Generator(nn.Module):
         nk = self.num_kernels
         for i in range(self.num_upsamples):
             nc, up = self.noise_convs[i], self.ups[i]
-            xs, xst = ops.conv1d(har, nc.wt(), nc.bias, K=nc.k, stride=nc.stride, pad=nc.padding, want_stats=True)
+            xs, xst = ops.conv1d(har, nc.wt(), nc.bias, K=nc.k, stride=nc.stride, pad=nc.padding, want_stats=True, wtc=nc.wtc())
             xs, _ = self.noise_res[i].run(xs, fcs, xst)
             x, st = ops.conv_transpose1d(x, up.wp(), up.bias, K=up.k, stride=up.stride, padding=up.padding, pre_act=ACT_LRELU,
-                                         slope=0.1, res=xs, reflect_left1=(i == self.num_upsamples - 1), want_stats=True)
+                                         slope=0.1, res=xs, reflect_left1=(i == self.num_upsamples - 1), want_stats=True,
+                                         wtc=up.wtc())
             x = _mrf(self.resblocks[i * nk:(i + 1) * nk], x, st, fcs, nk)
-        y, _ = ops.conv1d(x, self.conv_post.wt(), self.conv_post.bias, K=7, pad=3, pre_act=ACT_LRELU, slope=0.01)
+        y, _ = ops.conv1d(x, self.conv_post.wt(), self.conv_post.bias, K=7, pad=3, pre_act=ACT_LRELU, slope=0.01, wtc=self.conv_post.wtc())
         return ops.istft20_expsin(y).unsqueeze(1)
 
 
@@ -591,10 +614,10 @@ class HifiGenerator(nn.Module):
         nk = self.num_kernels
         for i in range(self.num_upsamples):
             nc, up = self.noise_convs[i], self.ups[i]
-            xs, xst = ops.conv1d(har, nc.wt(), nc.bias, K=nc.k, stride=nc.stride, pad=nc.padding, want_stats=True)
+            xs, xst = ops.conv1d(har, nc.wt(), nc.bias, K=nc.k, stride=nc.stride, pad=nc.padding, want_stats=True, wtc=nc.wtc())
             xs, _ = self.noise_res[i].run(xs, fcs, xst)
             x, st = ops.conv_transpose1d(x, up.wp(), up.bias, K=up.k, stride=up.stride, padding=up.padding, pre_act=ACT_SNAKE,
-                                         alpha=self.alphas[i], res=xs, want_stats=True)
+                                         alpha=self.alphas[i], res=xs, want_stats=True, wtc=up.wtc())
             x = _mrf(self.resblocks[i * nk:(i + 1) * nk], x, st, fcs, nk)
         y, _ = ops.conv1d(x, self.conv_post.wt(), self.conv_post.bias, K=7, pad=3, pre_act=ACT_SNAKE,
                           alpha=self.alphas[self.num_upsamples], out_act=ACT_TANH)
@@ -640,7 +663,7 @@ class Decoder(nn.Module):
         Ccat = Cx + 64 + 2
         bufs = [ops.empty(B, Ccat, T, device=dev), ops.empty(B, Ccat, T, device=dev)]
         ar = self.asr_res[0]
-        ops.conv1d(cat0[:, :Ca], ar.wt(), ar.bias, K=1, out=bufs[0][:, Cx:Cx + 64])
+        ops.conv1d(cat0[:, :Ca], ar.wt(), ar.bias, K=1, out=bufs[0][:, Cx:Cx + 64], wtc=ar.wtc())
         bufs[0][:, Cx + 64:].copy_(cat0[:, Ca:])
         bufs[1][:, Cx:].copy_(bufs[0][:, Cx:])
         self.encode.run(cat0, fcs, out=bufs[0][:, :Cx])

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -85,10 +86,29 @@ def _fill_conv_args(a: ConvArgs, x, wt, bias, y, *, K, stride, dil, pad, Lq, y_l
     a.dup_q0_to = -1
 
 
+USE_TC = os.environ.get("ST2_TC", "1") != "0"   # tensor-core (tcgen05) conv path where a wtc buffer is given
+TC_MIN_WORK = 1 << 22                            # below this many MACs per utterance the SIMT kernel is used
+
+
+def conv_tc_supported(Cin, Cout, K, stride, dil) -> bool:
+    return bool(L.load().st2_conv_tc_supported(Cin, Cout, K, stride, dil))
+
+
+def conv_tc_weight_layout(w: torch.Tensor) -> torch.Tensor:
+    """folded fp32 [Cout,Cin,K] -> bf16 hi/lo stage blocks for st2_conv1d_tc (opaque uint8 buffer)"""
+    w = w.detach().contiguous()
+    co, ci, k = w.shape
+    nbytes = int(L.load().st2_conv_tc_weight_bytes(co, ci, k))
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    L.call("st2_conv_tc_weight_layout", ptr(w), ptr(out), co, ci, k, stream_ptr())
+    return out
+
+
 def conv1d(x, wt, bias=None, *, K, stride=1, dil=1, pad=0, pre=None, pre_act=ACT_NONE, slope=0.0, alpha=None,
            res=None, res_shift=0, out_div=1.0, accum_mode=0, accum_div=1.0, out_act=ACT_NONE, out=None,
-           want_stats=False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+           want_stats=False, wtc=None, tc_max_ctas=0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Fused Conv1d (see include/styletts2_b200.h).  wt is the [Cin,K,Cout] layout.
+    wtc: optional tensor-core weight buffer (conv_tc_weight_layout) -> tcgen05 path when supported.
     Returns (y [B,Cout,Lout], stats [B,Cout,nparts,3] or None)."""
     x = _cl(x)
     B, Cin, Lin = x.shape
@@ -104,12 +124,25 @@ def conv1d(x, wt, bias=None, *, K, stride=1, dil=1, pad=0, pre=None, pre_act=ACT
     _fill_conv_args(a, x, wt, bias, out, K=K, stride=stride, dil=dil, pad=pad, Lq=Lout, y_len=Lout, pre=pre,
                     pre_act=pre_act, slope=slope, alpha=alpha, res=res, res_shift=res_shift, out_div=out_div,
                     accum_mode=accum_mode, accum_div=accum_div, out_act=out_act, stats=stats, nparts=nparts)
-    L.call("st2_conv1d", C.byref(a), stream_ptr())
+    if wtc is not None and USE_TC and stride == 1 and Cin * Cout * K * Lout >= TC_MIN_WORK:
+        L.call("st2_conv1d_tc", C.byref(a), ptr(wtc), tc_max_ctas, stream_ptr())
+    else:
+        L.call("st2_conv1d", C.byref(a), stream_ptr())
     return out, stats
 
 
+def convT_tc_weight_layout(w: torch.Tensor, stride: int, padding: int) -> torch.Tensor:
+    """folded fp32 ConvTranspose1d weight [Cin,Cout,K] -> per-phase tensor-core blocks"""
+    w = w.detach().contiguous()
+    ci, co, k = w.shape
+    nbytes = int(L.load().st2_convT_tc_weight_bytes(ci, co, k, stride))
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    L.call("st2_convT_tc_weight_layout", ptr(w), ptr(out), ci, co, k, stride, padding, stream_ptr())
+    return out
+
+
 def conv_transpose1d(x, wp, bias, *, K, stride, padding, pre_act=ACT_NONE, slope=0.0, alpha=None, res=None,
-                     reflect_left1=False, want_stats=False, out=None):
+                     reflect_left1=False, want_stats=False, out=None, wtc=None):
     """Polyphase ConvTranspose1d; wp is the [S,Cin,J,Cout] layout; output length Lin*S (+1 if reflect)."""
     x = _cl(x)
     B, Cin, Lin = x.shape
@@ -125,7 +158,10 @@ def conv_transpose1d(x, wp, bias, *, K, stride, padding, pre_act=ACT_NONE, slope
     _fill_conv_args(a, x, wp, bias, out, K=1, stride=1, dil=1, pad=0, Lq=Lin, y_len=Lout, pre=None, pre_act=pre_act,
                     slope=slope, alpha=alpha, res=res, res_shift=0, out_div=1.0, accum_mode=0, accum_div=1.0,
                     out_act=ACT_NONE, stats=stats, nparts=nparts)
-    L.call("st2_conv_transpose1d", C.byref(a), ptr(wp), K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
+    if wtc is not None and USE_TC:
+        L.call("st2_conv_transpose1d_tc", C.byref(a), ptr(wtc), K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
+    else:
+        L.call("st2_conv_transpose1d", C.byref(a), ptr(wp), K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
     return out, stats
 
 

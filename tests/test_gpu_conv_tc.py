@@ -1,0 +1,103 @@
+"""GPU tier: the tcgen05 / TMEM tensor-core Conv1d (bf16 hi/lo split, 3 MMAs per product, fp32 accumulate)
+against fp32 torch.  Tolerance 1e-4 relative to the output scale (measured ~1e-5; single bf16 would be ~1e-2)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import styletts2_oracle as O
+from util import maxdiff, record
+
+D = "cuda:0"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+TC_CASES = [
+    # B, Cin, Cout, K, dil, L, max_ctas
+    (1, 32, 128, 1, 1, 256, 0),      # single MMA group, no taps, no tail
+    (1, 32, 128, 3, 1, 256, 0),      # taps (descriptor row shifts)
+    (2, 128, 128, 3, 1, 700, 0),     # several ci blocks, tail tile
+    (2, 128, 128, 7, 3, 1000, 0),
+    (2, 256, 256, 11, 5, 1300, 0),   # two co blocks, max window
+    (3, 64, 64, 7, 5, 2000, 0),      # Cout padded to 128
+    (2, 48, 32, 11, 1, 900, 0),      # Cin, Cout padded
+    (4, 128, 128, 3, 1, 3000, 5),    # persistent loop: 48 tiles on 5 CTAs (TMEM double buffering, phase wrap)
+]
+
+
+@pytest.mark.parametrize("cfg", TC_CASES)
+def test_conv1d_tc_matches_fp32(cfg):
+    from styletts2_b200 import ops
+    from styletts2_b200.lib import ACT_SNAKE
+    B, Cin, Cout, K, d, L, max_ctas = cfg
+    x, w, bias = rnd(B, Cin, L, seed=1), rnd(Cout, Cin, K, seed=2, scale=1 / math.sqrt(Cin * K)), rnd(Cout, seed=3)
+    a, b = 1 + 0.3 * rnd(B, Cin, seed=4), 0.2 * rnd(B, Cin, seed=5)
+    alpha = 1 + 0.3 * torch.rand(1, Cin, 1, generator=torch.Generator().manual_seed(6))
+    res = rnd(B, Cout, L, seed=7)
+    z = a[:, :, None] * x + b[:, :, None]
+    z = z + (1 / alpha) * torch.sin(alpha * z) ** 2
+    pad = O.get_padding(K, d)
+    ref = F.conv1d(z, w, bias, 1, pad, d) + res
+    wd = w.to(D)
+    y, st = ops.conv1d(x.to(D), ops.conv_weight_layout(wd), bias.to(D), K=K, dil=d, pad=pad, pre=(a.to(D).contiguous(), b.to(D).contiguous()),
+                       pre_act=ACT_SNAKE, alpha=alpha.to(D), res=res.to(D), want_stats=True, wtc=ops.conv_tc_weight_layout(wd),
+                       tc_max_ctas=max_ctas)
+    torch.cuda.synchronize()
+    r = maxdiff(y, ref) / float(ref.abs().max())
+    record("conv1d_tc", cfg=str(cfg), rel_err=r)
+    assert r < 1e-4, r
+    gb = torch.zeros(B, 2 * Cout, device=D)
+    ca, cb = ops.adain_coef(st, gb)
+    ea = 1 / torch.sqrt(ref.var(-1, unbiased=False) + 1e-5)
+    assert maxdiff(ca, ea) / float(ea.abs().max()) < 1e-4 and maxdiff(cb, -ref.mean(-1) * ea) < 1e-3
+
+
+def test_conv1d_tc_mrf_accumulate_matches_simt():
+    from styletts2_b200 import ops
+    B, C, K, L = 2, 128, 3, 1500
+    x = rnd(B, C, L, seed=1)
+    ws = [rnd(C, C, K, seed=10 + i, scale=0.1) for i in range(3)]
+    ref = (F.conv1d(x, ws[0], None, 1, 1) + F.conv1d(x, ws[1], None, 1, 1) + F.conv1d(x, ws[2], None, 1, 1)) / 3
+    acc = torch.empty(B, C, L, device=D)
+    for i in range(3):
+        wd = ws[i].to(D)
+        ops.conv1d(x.to(D), ops.conv_weight_layout(wd), None, K=K, pad=1, out=acc, accum_mode=0 if i == 0 else (2 if i == 2 else 1),
+                   accum_div=3.0, wtc=ops.conv_tc_weight_layout(wd))
+    assert maxdiff(acc, ref) / float(ref.abs().max()) < 1e-4
+
+
+CONVT_TC = [  # Cin, Cout, K, S, P, OP, L, reflect
+    (256, 128, 12, 6, 3, 0, 700, True),
+    (512, 256, 20, 10, 5, 0, 300, False),
+    (128, 64, 6, 3, 2, 1, 1000, False),
+    (64, 32, 4, 2, 1, 0, 2000, False),
+]
+
+
+@pytest.mark.parametrize("cfg", CONVT_TC)
+def test_conv_transpose1d_tc_matches_fp32(cfg):
+    from styletts2_b200 import ops
+    from styletts2_b200.lib import ACT_LRELU
+    Cin, Cout, K, S, P, OP, L, reflect = cfg
+    x, w, b = rnd(2, Cin, L, seed=1), rnd(Cin, Cout, K, seed=2, scale=1 / math.sqrt(Cin * 2)), rnd(Cout, seed=3)
+    ref = F.conv_transpose1d(F.leaky_relu(x, 0.1), w, b, stride=S, padding=P, output_padding=OP)
+    if reflect:
+        ref = F.pad(ref, (1, 0), mode="reflect")
+    res = rnd(2, Cout, ref.shape[-1], seed=4)
+    ref = ref + res
+    wd = w.to(D)
+    y, st = ops.conv_transpose1d(x.to(D), ops.convT_weight_layout(wd, S, P), b.to(D), K=K, stride=S, padding=P, pre_act=ACT_LRELU,
+                                 slope=0.1, res=res.to(D), reflect_left1=reflect, want_stats=True,
+                                 wtc=ops.convT_tc_weight_layout(wd, S, P))
+    assert y.shape == ref.shape
+    r = maxdiff(y, ref) / float(ref.abs().max())
+    assert r < 1e-4, r
+    ca, cb = ops.adain_coef(st, torch.zeros(2, 2 * Cout, device=D))
+    ea = 1 / torch.sqrt(ref.var(-1, unbiased=False) + 1e-5)
+    assert maxdiff(ca, ea) / float(ea.abs().max()) < 1e-4 and maxdiff(cb, -ref.mean(-1) * ea) < 1e-3
