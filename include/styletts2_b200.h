@@ -92,12 +92,16 @@ int st2_conv_stats_parts(int Lq);
 /* Tensor-core path of the same fused Conv1d (stride 1): tcgen05 implicit GEMM with TMEM accumulators,
  * bf16 hi/lo split operands (hi*hi + hi*lo + lo*hi, fp32 accumulate), weights streamed by 1-D TMA bulk
  * copies.  `wtc` is the st2_conv_tc_weight_layout buffer (st2_conv_tc_weight_bytes bytes) built from the
- * folded fp32 weight [Cout,Cin,K].  a->w is ignored; every other field means what it means for st2_conv1d.
+ * folded fp32 weight [Cout,Cin,K].  a->w is ignored; every other field means what it means for st2_conv1d,
+ * except that it writes TWO statistics partials per 256-column tile (stats_nparts >= offset + 2*ceil(Lq/256)).
  * max_ctas > 0 caps the persistent grid (testing).  Same call sites as st2_conv1d. */
 long long st2_conv_tc_weight_bytes(int Cout, int Cin, int K);
 int st2_conv_tc_weight_layout(const float* w, void* out, int Cout, int Cin, int K, void* stream);
 int st2_conv_tc_supported(int Cin, int Cout, int K, int stride, int dil);
 int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int max_ctas, void* stream);
+/* Profiling aid: when set to a device buffer of 4*16*8 int64, CTA 0 of st2_conv1d_tc records per-role cycle
+ * counters for its first 16 tiles (role 0 MMA, 1 weight producer, 2 stagers, 3 epilogue); NULL disables. */
+int st2_debug_set_trace(void* buf);
 /* Polyphase ConvTranspose1d on the same tensor-core kernel (one launch per phase); wtc from
  * st2_convT_tc_weight_layout (st2_convT_tc_weight_bytes bytes).  Arguments as st2_conv_transpose1d. */
 long long st2_convT_tc_weight_bytes(int Cin, int Cout, int K, int S);

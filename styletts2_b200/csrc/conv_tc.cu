@@ -21,7 +21,8 @@
 //    memory for coalesced row stores and fuses bias, residual, MRF accumulation and the InstanceNorm
 //    partial statistics (count, mean, M2) exactly like the SIMT kernel.
 //  * Warp roles: warp 0 = TMEM alloc + single-thread MMA issue, warp 1 = weight TMA producer,
-//    warps 2-9 = activation stagers, warps 10-13 = epilogue.  Persistent CTAs (one per SM) loop over tiles.
+//    warps 2-11 = activation stagers, warps 12-19 = epilogue.
+//    Persistent CTAs (one per SM) loop over tiles.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -37,22 +38,32 @@ constexpr int CB = 32;
 constexpr int W_STAGES = 4;
 constexpr int W_STAGE_BYTES = 2 * 4 * TM * 16;  // (hi|lo) x 4 k-chunks x 128 co x 16 B
 constexpr int RW_MAX = 312;                     // TN + (K-1)*dil rounded up to 8, max
-constexpr int ACT_HALF_BYTES = 4 * RW_MAX * 16; // one of hi / lo for one 32-channel block
+constexpr int RWP_MAX = RW_MAX + 2;             // chunk pitch in rows: == 2 (mod 8) -> conflict-free 128-bit staging stores
+constexpr int ACT_HALF_BYTES = 4 * RWP_MAX * 16; // one of hi / lo for one 32-channel block
 constexpr int ACT_BUF_BYTES = 2 * ACT_HALF_BYTES;
 constexpr int CIN_PAD_MAX = 1120;
-constexpr int NUM_STAGERS = 256;
-constexpr int NUM_EPI = 128;
-constexpr int THREADS = 64 + NUM_STAGERS + NUM_EPI;  // 448
+constexpr int NUM_STAGERS = 320;                // 10 warps
+constexpr int NUM_EPI = 256;                    // 8 warps: two per TMEM lane quarter (each takes half of the columns)
+constexpr int THREADS = 64 + NUM_STAGERS + NUM_EPI;  // 640 = 20 warps (register allocation granularity: 4 warps)
+constexpr int STG_RG = NUM_STAGERS / 4;         // 80 frame-row groups
+constexpr int TPITCH = 36;                      // epilogue transpose row pitch (floats), 16-byte aligned rows
 
 constexpr int SM_W = 0;
 constexpr int SM_ACT = SM_W + W_STAGES * W_STAGE_BYTES;
 constexpr int SM_COEF = SM_ACT + 2 * ACT_BUF_BYTES;
-constexpr int SM_EPI = SM_COEF + 3 * CIN_PAD_MAX * 4;
-constexpr int SM_BAR = SM_EPI + 4 * 32 * 33 * 4;
+constexpr int SM_EPI = SM_COEF + 4 * CIN_PAD_MAX * 4;
+constexpr int SM_BAR = SM_EPI + 8 * (32 * TPITCH + 32) * 4;
 constexpr int SM_TOTAL = SM_BAR + 256;
 
 // barrier slots (8 B each) inside SM_BAR
 constexpr int B_WFULL = 0, B_WEMPTY = 4, B_AFULL = 8, B_AEMPTY = 10, B_TFULL = 12, B_TEMPTY = 14, B_COUNT = 16;
+
+// Optional per-role cycle trace of CTA 0 (debug/profiling aid; null in production).
+__device__ long long* g_trace = nullptr;
+constexpr int TRACE_TILES = 16, TRACE_K = 8;  // [role 4][tile 16][8 counters]
+__device__ __forceinline__ void trace_put(int role, int it, int k, long long v) {
+  if (g_trace && blockIdx.x == 0 && it < TRACE_TILES) g_trace[(role * TRACE_TILES + it) * TRACE_K + k] = v;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -81,6 +92,12 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+__device__ __forceinline__ long long mbar_wait_timed(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+  }
+  return clock64() - t0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
@@ -156,9 +173,70 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stager inner work: AdaIN affine + activation + bf16 hi/lo split + two 128-bit stores for one frame row
+// (8 channels of one K-chunk).  Templated on the activation so the per-element code has no branches.
+template <int ACT>
+__device__ __forceinline__ void stage_row(const float (&x)[8], const float (&pa)[8], const float (&pb)[8], const float (&al)[8],
+                                          const float (&ia)[8], float slope, bool inb, uint8_t* hi_dst, uint8_t* lo_dst) {
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float z = fmaf(x[j], pa[j], pb[j]);
+    if (ACT == ST2_ACT_SNAKE) {
+      const float sn = __sinf(al[j] * z);
+      z = fmaf(ia[j], sn * sn, z);
+    } else if (ACT == ST2_ACT_LRELU) {
+      z = z > 0.f ? z : z * slope;
+    }
+    v[j] = inb ? z : 0.f;  // zero padding applies AFTER the activation
+  }
+  uint32_t hp[4], lp[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    hp[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+    const float h0 = __uint_as_float(hp[q] << 16), h1 = __uint_as_float(hp[q] & 0xFFFF0000u);
+    lp[q] = pack_bf16(v[2 * q] - h0, v[2 * q + 1] - h1);
+  }
+  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+}
+
+// Epilogue row loop for one 32x32 accumulator block already transposed into T: row r of the block is output
+// channel (co_base + r); lane = column.  yp points at (row 0, this lane's column); rv[] holds the 32 residual
+// values of this lane's column (prefetched before the TMEM load so their latency is hidden).
+template <bool RES, int ACC, bool STATS>
+__device__ __forceinline__ void epi_rows(float* T, const float* bsm, float* yp, const float (&rv)[32], long long ystride,
+                                         int rmax, bool tv, int lane, float out_div, float acc_div) {
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 8) {
+    if (r0 < rmax) {
+      float yo[8];
+      if (ACC) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) yo[i] = (tv && (r0 + i) < rmax) ? yp[i * ystride] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + i;
+        float val = T[r * TPITCH + lane] + bsm[r];
+        if (RES) val += rv[r];
+        if (out_div != 1.0f) val = __fdiv_rn(val, out_div);
+        if (ACC == 1) val = yo[i] + val;
+        if (ACC == 2) val = __fdiv_rn(yo[i] + val, acc_div);
+        if (tv && r < rmax) yp[i * ystride] = val;
+        if (STATS) T[r * TPITCH + lane] = val;
+      }
+      yp += 8 * ystride;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int ncb, const int RW, const int ntiles,
                  const int n_tq, const int n_cob) {
+  // RW = window rows (TN + (K-1)*dil, rounded up to 8); RWP = chunk pitch in rows
+  const int RWP = RW + 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -190,22 +268,24 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     // ================================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc();
-      const uint32_t lbo_a = TM * 16, lbo_b = (uint32_t)RW * 16;
+      const uint32_t lbo_a = TM * 16, lbo_b = (uint32_t)RWP * 16;
       int ws = 0, wph = 0, as = 0, aph = 0;
+      auto wait_pumping = [&](uint32_t bar, uint32_t parity) -> long long { return mbar_wait_timed(bar, parity); };
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
-        mbar_wait(BAR(B_TEMPTY + buf), ((it >> 1) & 1) ^ 1);
+        const long long tt0 = clock64();
+        long long w_te = wait_pumping(BAR(B_TEMPTY + buf), ((it >> 1) & 1) ^ 1), w_af = 0, w_wf = 0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * TN;
         uint32_t first = 1;
         for (int cb = 0; cb < ncb; ++cb) {
-          mbar_wait(BAR(B_AFULL + as), aph);
+          w_af += wait_pumping(BAR(B_AFULL + as), aph);
           tc_fence_after();
           const uint32_t act_hi = sbase + SM_ACT + as * ACT_BUF_BYTES;
           const uint32_t act_lo = act_hi + ACT_HALF_BYTES;
           for (int tap = 0; tap < K; ++tap) {
-            mbar_wait(BAR(B_WFULL + ws), wph);
+            w_wf += wait_pumping(BAR(B_WFULL + ws), wph);
             tc_fence_after();
             const uint32_t w_hi = sbase + SM_W + ws * W_STAGE_BYTES;
             const uint32_t w_lo = w_hi + W_STAGE_BYTES / 2;
@@ -228,6 +308,8 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           if (++as == 2) { as = 0; aph ^= 1; }
         }
         tc_commit(BAR(B_TFULL + buf));
+        trace_put(0, it, 0, tt0); trace_put(0, it, 1, clock64()); trace_put(0, it, 2, w_te); trace_put(0, it, 3, w_af);
+        trace_put(0, it, 4, w_wf);
       }
     }
   } else if (warp == 1) {
@@ -239,8 +321,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
         for (int cb = 0; cb < ncb; ++cb) {
           for (int tap = 0; tap < K; ++tap) {
             mbar_wait(BAR(B_WEMPTY + ws), wph ^ 1);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(wtc) +
-                                 ((size_t)((tap * n_cob + tc_.cob) * ncb + cb)) * W_STAGE_BYTES;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(wtc) + ((size_t)((tap * n_cob + tc_.cob) * ncb + cb)) * W_STAGE_BYTES;
             mbar_expect_tx(BAR(B_WFULL + ws), W_STAGE_BYTES);
             bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, W_STAGE_BYTES, BAR(B_WFULL + ws));
             if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
@@ -250,22 +331,32 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     }
   } else if (warp < 2 + NUM_STAGERS / 32) {
     // ================================================================ activation stagers
-    const int st = tid - 64;  // 0..255
+    // thread -> one 8-channel K-chunk (kc) and every 64th frame row: the AdaIN / Snake coefficients of its 8
+    // channels live in registers, all loads of a block are issued before any is consumed.
+    const int st = tid - 64;  // 0..319
+    const int kc = st & 3, rg = st >> 2;  // lanes: 4 K-chunks x 8 consecutive frames (32-byte segments)
+    const int Lin_ = a.Lin, pre_act_ = a.pre_act;
+    const float slope_ = a.pre_slope;
     float* coef = reinterpret_cast<float*>(smem + SM_COEF);
     const int cin_pad = ncb * CB;
     int as = 0, aph = 0;
     int last_b = -1;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int sit = 0;
+    constexpr int NR = (RW_MAX + STG_RG - 1) / STG_RG;  // 6 row iterations max
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++sit) {
       const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
+      const long long stt0 = clock64();
+      long long w_ae = 0;
       if (tc_.b != last_b) {
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));  // everybody done reading the old table
         for (int c = st; c < cin_pad; c += NUM_STAGERS) {
-          float pa = 1.f, pb = 0.f, al = 1.f;
+          float pa = 0.f, pb = 0.f, al = 1.f;  // padded channels stage exact zeros
           if (c < a.Cin) {
+            pa = 1.f;
             if (a.pre_a) { pa = a.pre_a[tc_.b * a.Cin + c]; pb = a.pre_b[tc_.b * a.Cin + c]; }
             if (a.pre_act == ST2_ACT_SNAKE) al = a.pre_alpha[c];
           }
-          coef[c] = pa; coef[CIN_PAD_MAX + c] = pb; coef[2 * CIN_PAD_MAX + c] = al;
+          coef[c] = pa; coef[CIN_PAD_MAX + c] = pb; coef[2 * CIN_PAD_MAX + c] = al; coef[3 * CIN_PAD_MAX + c] = 1.0f / al;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));
         last_b = tc_.b;
@@ -273,139 +364,165 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       const float* xb = a.x + (long long)tc_.b * a.x_bstride;
       const int g0 = tc_.tq * TN - a.pad;  // global time of window row 0
       for (int cb = 0; cb < ncb; ++cb) {
-        mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
+        const int c0 = cb * CB + kc * 8;
+        float pa[8], pb[8], al[8], ia[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          pa[j] = coef[c0 + j]; pb[j] = coef[CIN_PAD_MAX + c0 + j]; al[j] = coef[2 * CIN_PAD_MAX + c0 + j];
+          ia[j] = coef[3 * CIN_PAD_MAX + c0 + j];
+        }
+        // 8 channel rows of this K-chunk: base pointer + j*Lin (channels beyond Cin are clamped; their pa=pb=0)
+        const int cclamp = min(c0, max(a.Cin - 8, 0));
+        const float* xc0 = xb + (long long)cclamp * Lin_;
+        const int jmax = a.Cin - 1 - cclamp;  // last valid j offset (>= 0)
         uint8_t* hi = smem + SM_ACT + as * ACT_BUF_BYTES;
         uint8_t* lo = hi + ACT_HALF_BYTES;
-        for (int r = st; r < RW; r += NUM_STAGERS) {
+        // all loads of this thread (up to 6 frame rows x 8 channels) are in flight before the buffer wait / first use
+        float xv[NR][8];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+          const int r = rg + STG_RG * i;
           const int g = g0 + r;
-          const bool inb = (g >= 0) && (g < a.Lin);
-          const int cbase = cb * CB;
-          float xv[CB];
-          // all 32 channel loads of this frame are issued before any is consumed (memory-level parallelism)
+          const bool ok = (r < RW) && (g >= 0) && (g < Lin_);
 #pragma unroll
-          for (int q = 0; q < CB; ++q) {
-            const int c = cbase + q;
-            xv[q] = (inb && c < a.Cin) ? __ldg(xb + (long long)c * a.Lin + g) : 0.f;
-          }
+          for (int j = 0; j < 8; ++j) xv[i][j] = ok ? __ldg(xc0 + (long long)min(j + (c0 - cclamp), jmax) * Lin_ + g) : 0.f;
+        }
+        w_ae += mbar_wait_timed(BAR(B_AEMPTY + as), aph ^ 1);
 #pragma unroll
-          for (int kc = 0; kc < 4; ++kc) {
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = cbase + kc * 8 + j;
-              float z = 0.f;
-              if (inb && c < a.Cin) {
-                z = fmaf(xv[kc * 8 + j], coef[c], coef[CIN_PAD_MAX + c]);
-                if (a.pre_act == ST2_ACT_SNAKE) {
-                  const float al = coef[2 * CIN_PAD_MAX + c];
-                  const float sn = __sinf(al * z);
-                  z = z + __fdividef(1.0f, al) * (sn * sn);
-                } else if (a.pre_act == ST2_ACT_LRELU) {
-                  z = z > 0.f ? z : z * a.pre_slope;
-                }
-              }
-              v[j] = z;
-            }
-            uint4 h4, l4;
-            float h[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-            h4.x = pack_bf16(h[0], h[1]); h4.y = pack_bf16(h[2], h[3]); h4.z = pack_bf16(h[4], h[5]); h4.w = pack_bf16(h[6], h[7]);
-            l4.x = pack_bf16(v[0] - h[0], v[1] - h[1]); l4.y = pack_bf16(v[2] - h[2], v[3] - h[3]);
-            l4.z = pack_bf16(v[4] - h[4], v[5] - h[5]); l4.w = pack_bf16(v[6] - h[6], v[7] - h[7]);
-            *reinterpret_cast<uint4*>(hi + (size_t)(kc * RW + r) * 16) = h4;
-            *reinterpret_cast<uint4*>(lo + (size_t)(kc * RW + r) * 16) = l4;
+        for (int i = 0; i < NR; ++i) {
+          const int r = rg + STG_RG * i;
+          if (r < RW) {
+            const int g = g0 + r;
+            const bool inb = (g >= 0) && (g < Lin_);
+            uint8_t* hd = hi + (size_t)(kc * RWP + r) * 16;
+            uint8_t* ld = lo + (size_t)(kc * RWP + r) * 16;
+            if (pre_act_ == ST2_ACT_SNAKE) stage_row<ST2_ACT_SNAKE>(xv[i], pa, pb, al, ia, slope_, inb, hd, ld);
+            else if (pre_act_ == ST2_ACT_LRELU) stage_row<ST2_ACT_LRELU>(xv[i], pa, pb, al, ia, slope_, inb, hd, ld);
+            else stage_row<ST2_ACT_NONE>(xv[i], pa, pb, al, ia, slope_, inb, hd, ld);
           }
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(BAR(B_AFULL + as));
         if (++as == 2) { as = 0; aph ^= 1; }
       }
+      if (st == 0) { trace_put(2, sit, 0, stt0); trace_put(2, sit, 1, clock64()); trace_put(2, sit, 2, w_ae); }
     }
   } else {
-    // ================================================================ epilogue
-    const int ew = warp & 3;  // TMEM lane quarter this warp may access
-    float* T = reinterpret_cast<float*>(smem + SM_EPI) + ew * 32 * 33;
+    // ================================================================ epilogue (8 warps)
+    const int ewi = warp - (2 + NUM_STAGERS / 32);  // 0..7
+    const int ew = warp & 3;                         // TMEM lane quarter this warp may access
+    const int half = ewi >> 2;                       // which 128 columns of the tile this warp handles
+    float* T = reinterpret_cast<float*>(smem + SM_EPI) + ewi * (32 * TPITCH + 32);
+    float* bsm = T + 32 * TPITCH;
+    const int y_len_ = a.y_len, res_len_ = a.res_len, acc_ = a.accum_mode, out_act_ = a.out_act, Cout_ = a.Cout, Lq_ = a.Lq;
+    const int ytst_ = a.y_tstride, ytoff_ = a.y_toffset, rshift_ = a.res_shift;
+    const float out_div_ = a.out_div, acc_div_ = a.accum_div;
+    const bool has_stats = a.stats != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
       const int buf = it & 1;
-      mbar_wait(BAR(B_TFULL + buf), (it >> 1) & 1);
-      tc_fence_after();
       const int co_base = tc_.cob * TM + ew * 32;
       const int t0 = tc_.tq * TN;
-      const int ncols = min(TN, a.Lq - t0);
-      float* yb = a.y + (long long)tc_.b * a.y_bstride;
-      // running (count, mean, M2) of row (co_base + lane)
-      float s_n = 0.f, s_mean = 0.f, s_m2 = 0.f;
-      for (int c0 = 0; c0 < TN; c0 += 32) {
+      const int ncols = min(TN, Lq_ - t0);
+      const int rmax = min(32, Cout_ - co_base);  // warp-uniform (may be <= 0 for padded channel blocks)
+      bsm[lane] = (a.bias && lane < rmax) ? a.bias[co_base + lane] : 0.f;
+      const long long ett0 = clock64();
+      const long long w_tf = mbar_wait_timed(BAR(B_TFULL + buf), (it >> 1) & 1);
+      tc_fence_after();
+      float* yb = a.y + (long long)tc_.b * a.y_bstride + (long long)co_base * y_len_;
+      const float* rb = a.res ? a.res + (long long)tc_.b * a.res_bstride + (long long)co_base * res_len_ : nullptr;
+      float s_n = 0.f, s_mean = 0.f, s_m2 = 0.f;  // running (count, mean, M2) of row (co_base + lane)
+      long long tr_ld = 0, tr_st = 0, tr_ss = 0;
+      for (int c0 = half * (TN / 2); c0 < (half + 1) * (TN / 2); c0 += 32) {
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + c0), v);
-        if (c0 >= ncols) continue;
+        const long long q0 = clock64();
+        float rv[32];
+        {
+          const int tcol = t0 + c0 + lane;
+          const bool okc = (c0 + lane) < ncols;
+          const float* rp0 = rb ? rb + ((tcol * ytst_ + ytoff_) >> rshift_) : nullptr;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) T[lane * 33 + j] = v[j];
+          for (int r = 0; r < 32; ++r) rv[r] = (rb && okc && r < rmax) ? __ldg(rp0 + (long long)r * res_len_) : 0.f;
+        }
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + c0), v);
+        const long long q1 = clock64();
+        tr_ld += q1 - q0;
+        if (c0 >= ncols || rmax <= 0) continue;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(&T[lane * TPITCH + 4 * q]) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
         const int t = t0 + c0 + lane;
         const bool tv = (c0 + lane) < ncols;
-        const int oidx = t * a.y_tstride + a.y_toffset;
-        const int rmax = min(32, a.Cout - co_base);  // warp-uniform
-        for (int r0 = 0; r0 < rmax; r0 += 8) {
-          float rv[8], yo[8];
-          // residual / accumulator loads of 8 rows are in flight together
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int co = co_base + r0 + i;
-            const bool ok = tv && (r0 + i) < rmax;
-            rv[i] = (ok && a.res) ? __ldg(a.res + (long long)tc_.b * a.res_bstride + (long long)co * a.res_len + (oidx >> a.res_shift)) : 0.f;
-            yo[i] = (ok && a.accum_mode) ? yb[(long long)co * a.y_len + oidx] : 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = r0 + i;
-            if (r >= rmax) break;
-            const int co = co_base + r;
-            float val = 0.f;
-            if (tv) {
-              val = T[r * 33 + lane] + (a.bias ? a.bias[co] : 0.f) + rv[i];
-              if (a.out_div != 1.0f) val = __fdiv_rn(val, a.out_div);
-              if (a.accum_mode == 1) val = yo[i] + val;
-              else if (a.accum_mode == 2) val = __fdiv_rn(yo[i] + val, a.accum_div);
-              if (a.out_act == ST2_ACT_TANH) val = tanhf(val);
-              yb[(long long)co * a.y_len + oidx] = val;
+        const int oidx = t * ytst_ + ytoff_;
+        const int ridx = oidx >> rshift_;
+        {
+          float* yp = yb + oidx;
+          const float* rp = rb ? rb + ridx : nullptr;
+          const long long ys = y_len_, rs = res_len_;
+          if (out_act_ == ST2_ACT_NONE) {
+#define EPI(RES_, ACC_, ST_) epi_rows<RES_, ACC_, ST_>(T, bsm, yp, rv, ys, rmax, tv, lane, out_div_, acc_div_)
+            if (has_stats) {
+              if (rb) { if (acc_ == 0) EPI(true, 0, true); else if (acc_ == 1) EPI(true, 1, true); else EPI(true, 2, true); }
+              else    { if (acc_ == 0) EPI(false, 0, true); else if (acc_ == 1) EPI(false, 1, true); else EPI(false, 2, true); }
+            } else {
+              if (rb) { if (acc_ == 0) EPI(true, 0, false); else if (acc_ == 1) EPI(true, 1, false); else EPI(true, 2, false); }
+              else    { if (acc_ == 0) EPI(false, 0, false); else if (acc_ == 1) EPI(false, 1, false); else EPI(false, 2, false); }
             }
-            if (a.stats) T[r * 33 + lane] = val;
+#undef EPI
+          } else {  // rare generic path (output activation)
+            for (int r = 0; r < rmax; ++r) {
+              float val = 0.f;
+              if (tv) {
+                val = T[r * TPITCH + lane] + bsm[r];
+                if (rb) val += rv[r];
+                if (out_div_ != 1.0f) val = __fdiv_rn(val, out_div_);
+                if (acc_ == 1) val = yp[(long long)r * ys] + val;
+                else if (acc_ == 2) val = __fdiv_rn(yp[(long long)r * ys] + val, acc_div_);
+                if (out_act_ == ST2_ACT_TANH) val = tanhf(val);
+                yp[(long long)r * ys] = val;
+              }
+              if (has_stats) T[r * TPITCH + lane] = val;
+            }
           }
         }
+        const long long q2 = clock64();
+        tr_st += q2 - q1;
         // ReflectionPad1d((1,0)) duplicate of the q==0 column (istftnet.py:365-366): value differs by its residual
         const bool dup_here = (a.dup_q0_to >= 0) && (t0 == 0) && (c0 == 0);
         float dupv = 0.f;
-        if (dup_here) {
-          const int co = co_base + lane;  // here each lane owns one row; column 0 of the accumulator block
-          if (co < a.Cout) {
-            float val = v[0] + (a.bias ? a.bias[co] : 0.f);
-            if (a.res) val += a.res[(long long)tc_.b * a.res_bstride + (long long)co * a.res_len + (a.dup_q0_to >> a.res_shift)];
-            if (a.out_div != 1.0f) val = __fdiv_rn(val, a.out_div);
-            float* p = yb + (long long)co * a.y_len + a.dup_q0_to;
-            if (a.accum_mode == 1) val = *p + val;
-            else if (a.accum_mode == 2) val = __fdiv_rn(*p + val, a.accum_div);
-            if (a.out_act == ST2_ACT_TANH) val = tanhf(val);
-            *p = val;
-            dupv = val;
-          }
+        if (dup_here && lane < rmax) {
+          float val = v[0] + bsm[lane];
+          if (rb) val += rb[(long long)lane * a.res_len + (a.dup_q0_to >> a.res_shift)];
+          if (a.out_div != 1.0f) val = __fdiv_rn(val, a.out_div);
+          float* p = yb + (long long)lane * a.y_len + a.dup_q0_to;
+          if (a.accum_mode == 1) val = *p + val;
+          else if (a.accum_mode == 2) val = __fdiv_rn(*p + val, a.accum_div);
+          if (a.out_act == ST2_ACT_TANH) val = tanhf(val);
+          *p = val;
+          dupv = val;
         }
-        if (a.stats) {
+        if (has_stats) {
           __syncwarp();
           const int nv = min(32, ncols - c0);
+          float w[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4*>(&T[lane * TPITCH + 4 * q]);
+            w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+          }
           float cs = 0.f;
-          for (int j = 0; j < nv; ++j) cs += T[lane * 33 + j];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) cs += (j < nv) ? w[j] : 0.f;
           const float cmean = cs / (float)nv;
           float cm2 = 0.f;
-          for (int j = 0; j < nv; ++j) {
-            const float d = T[lane * 33 + j] - cmean;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = (j < nv) ? w[j] - cmean : 0.f;
             cm2 = fmaf(d, d, cm2);
           }
-          // Chan merge
-          const float nn = s_n + (float)nv;
+          const float nn = s_n + (float)nv;  // Chan merge
           const float delta = cmean - s_mean;
           s_mean += delta * ((float)nv / nn);
           s_m2 += cm2 + delta * delta * (s_n * (float)nv / nn);
@@ -419,15 +536,17 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           }
         }
         __syncwarp();
+        tr_ss += clock64() - q2;
       }
       tc_fence_before();
       mbar_arrive(BAR(B_TEMPTY + buf));
-      if (a.stats) {
-        const int co = co_base + lane;
-        if (co < a.Cout) {
-          float* sp = a.stats + (((long long)tc_.b * a.Cout + co) * a.stats_nparts + a.stats_part_offset + tc_.tq) * 3;
-          sp[0] = s_n; sp[1] = s_mean; sp[2] = s_m2;
-        }
+      if (ewi == 0 && lane == 0) {
+        trace_put(3, it, 0, ett0); trace_put(3, it, 1, clock64()); trace_put(3, it, 2, w_tf);
+        trace_put(3, it, 3, tr_ld); trace_put(3, it, 4, tr_st); trace_put(3, it, 5, tr_ss);
+      }
+      if (a.stats && lane < rmax) {
+        float* sp = a.stats + (((long long)tc_.b * a.Cout + co_base + lane) * a.stats_nparts + a.stats_part_offset + 2 * tc_.tq + half) * 3;
+        sp[0] = s_n; sp[1] = s_mean; sp[2] = s_m2;
       }
     }
   }
@@ -533,9 +652,16 @@ int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int max_ctas, void* s
   ST2_REQUIRE(st2_conv_tc_supported(a->Cin, a->Cout, a->K, a->stride, a->dil), "st2_conv1d_tc", "unsupported shape");
   ST2_REQUIRE(a->pre_act != ST2_ACT_SNAKE || a->pre_alpha, "st2_conv1d_tc", "snake prologue needs alpha");
   const int n_tq = cdiv(a->Lq, tc::TN);
-  ST2_REQUIRE(!a->stats || a->stats_nparts >= a->stats_part_offset + n_tq, "st2_conv1d_tc", "stats buffer too small");
+  ST2_REQUIRE(!a->stats || a->stats_nparts >= a->stats_part_offset + 2 * n_tq, "st2_conv1d_tc", "stats buffer too small (2 partials per 256-column tile)");
   tc::launch_tc(*a, wtc, max_ctas, (cudaStream_t)stream);
   ST2_CHECK_LAUNCH("st2_conv1d_tc");
+  return 0;
+}
+
+int st2_debug_set_trace(void* buf) {
+  long long* p = (long long*)buf;
+  cudaError_t e = cudaMemcpyToSymbol(tc::g_trace, &p, sizeof(p));
+  if (e != cudaSuccess) { set_error("st2_debug_set_trace", e); return (int)e; }
   return 0;
 }
 
@@ -559,7 +685,7 @@ int st2_conv_transpose1d_tc(const st2_conv_args* a0, const void* wtc, int K, int
   ST2_REQUIRE(K > 0 && S > 0 && P >= 0, "st2_conv_transpose1d_tc", "bad shape");
   const int J = (K + S - 1) / S;
   ST2_REQUIRE(st2_conv_tc_supported(a0->Cin, a0->Cout, J, 1, 1), "st2_conv_transpose1d_tc", "unsupported shape");
-  const int parts = cdiv(a0->Lin, tc::TN);
+  const int parts = 2 * cdiv(a0->Lin, tc::TN);
   ST2_REQUIRE(!a0->stats || a0->stats_nparts >= S * parts, "st2_conv_transpose1d_tc", "stats buffer too small");
   const long long phase_bytes = st2_conv_tc_weight_bytes(a0->Cout, a0->Cin, J);
   for (int r = 0; r < S; ++r) {

@@ -59,6 +59,7 @@ SIGNATURES = {
     "st2_conv_tc_weight_layout": [_vp, _vp, _i, _i, _i, _vp],
     "st2_conv_tc_supported": [_i, _i, _i, _i, _i],
     "st2_conv1d_tc": [C.POINTER(ConvArgs), _vp, _i, _vp],
+    "st2_debug_set_trace": [_vp],
     "st2_convT_tc_weight_bytes": [_i, _i, _i, _i],
     "st2_convT_tc_weight_layout": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "st2_conv_transpose1d_tc": [C.POINTER(ConvArgs), _vp, _i, _i, _i, _i, _vp],

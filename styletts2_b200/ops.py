@@ -118,13 +118,14 @@ def conv1d(x, wt, bias=None, *, K, stride=1, dil=1, pad=0, pre=None, pre_act=ACT
     if out is None:
         out = empty(B, Cout, Lout, device=x.device)
     assert out.shape == (B, Cout, Lout) and out.stride(2) == 1 and out.stride(1) == Lout
-    nparts = stats_parts(Lout)
+    use_tc = wtc is not None and USE_TC and stride == 1 and Cin * Cout * K * Lout >= TC_MIN_WORK
+    nparts = stats_parts(Lout) * (2 if use_tc else 1)
     stats = empty(B, Cout, nparts, 3, device=x.device) if want_stats else None
     a = ConvArgs()
     _fill_conv_args(a, x, wt, bias, out, K=K, stride=stride, dil=dil, pad=pad, Lq=Lout, y_len=Lout, pre=pre,
                     pre_act=pre_act, slope=slope, alpha=alpha, res=res, res_shift=res_shift, out_div=out_div,
                     accum_mode=accum_mode, accum_div=accum_div, out_act=out_act, stats=stats, nparts=nparts)
-    if wtc is not None and USE_TC and stride == 1 and Cin * Cout * K * Lout >= TC_MIN_WORK:
+    if use_tc:
         L.call("st2_conv1d_tc", C.byref(a), ptr(wtc), tc_max_ctas, stream_ptr())
     else:
         L.call("st2_conv1d", C.byref(a), stream_ptr())
@@ -152,13 +153,14 @@ def conv_transpose1d(x, wp, bias, *, K, stride, padding, pre_act=ACT_NONE, slope
     Lout = Lin * S + (1 if reflect_left1 else 0)
     if out is None:
         out = empty(B, Cout, Lout, device=x.device)
-    nparts = S * stats_parts(Lin)
+    use_tc = wtc is not None and USE_TC
+    nparts = S * stats_parts(Lin) * (2 if use_tc else 1)
     stats = empty(B, Cout, nparts, 3, device=x.device) if want_stats else None
     a = ConvArgs()
     _fill_conv_args(a, x, wp, bias, out, K=1, stride=1, dil=1, pad=0, Lq=Lin, y_len=Lout, pre=None, pre_act=pre_act,
                     slope=slope, alpha=alpha, res=res, res_shift=0, out_div=1.0, accum_mode=0, accum_div=1.0,
                     out_act=ACT_NONE, stats=stats, nparts=nparts)
-    if wtc is not None and USE_TC:
+    if use_tc:
         L.call("st2_conv_transpose1d_tc", C.byref(a), ptr(wtc), K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
     else:
         L.call("st2_conv_transpose1d", C.byref(a), ptr(wp), K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
