@@ -129,11 +129,16 @@ def run_ours(args):
     wav_host = torch.empty(B, L, dtype=torch.float32).pin_memory()
     dec_ev = []
 
+    marks = []
+
     def step(inputs, timed_decoder=False):
         tokens, lengths, bert_dur, noise = inputs[:4]
         ref_s = inputs[4] if ms else None
+        mk = [] if timed_decoder else None
         out = syn.synthesize(tokens, lengths, bert_dur, noise, diffusion_steps=wl["steps"], ref_s=ref_s,
-                             pin_frames_per_token=wl["fpt"], decoder_events=dec_ev if timed_decoder else None)
+                             pin_frames_per_token=wl["fpt"], decoder_events=dec_ev if timed_decoder else None, stage_marks=mk)
+        if mk is not None:
+            marks.append(mk)
         return out["wav"]
 
     def barrier():
@@ -165,10 +170,15 @@ def run_ours(args):
     launches = lib.launch_count() - n0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     dec_ms = sum(a.elapsed_time(b) for a, b in dec_ev) / max(1, len(dec_ev))
+    stages = {}
+    for mk in marks:
+        for (n0_, e0_), (n1_, e1_) in zip(mk[:-1], mk[1:]):
+            stages[n1_] = stages.get(n1_, 0.0) + e0_.elapsed_time(e1_) / len(marks)
     if args.skip_e2e:
         if rank == 0:
             clocks.stop()
-            print(json.dumps({"profile_only": True, "ms_per_step": ms_total / args.steps, "decoder_ms": dec_ms, "gpu_launches": launches}))
+            print(json.dumps({"profile_only": True, "ms_per_step": ms_total / args.steps, "decoder_ms": dec_ms, "gpu_launches": launches,
+                              "stages_ms": stages}))
         return
     # ---- end to end through the public API with HOST buffers (`e2e`)
     def e2e_step():
@@ -206,6 +216,7 @@ def run_ours(args):
                    "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
+        "stages_ms": stages,
         "clocks": clk,
         "roofline": {"kernel": "decoder+vocoder chain (st2::conv1d_kernel<8> dominant)", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

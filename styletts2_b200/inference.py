@@ -41,7 +41,7 @@ class Synthesizer:
     @torch.no_grad()
     def synthesize(self, tokens, input_lengths, bert_dur, noise, *, diffusion_steps=5, embedding_scale=1.0, ref_s=None,
                    alpha=0.3, beta=0.7, rng: Optional[Dict] = None, forced_durations=None, pin_frames_per_token=None,
-                   return_all=False, decoder_events=None):
+                   return_all=False, decoder_events=None, stage_marks=None):
         """tokens [B,N] i64, input_lengths [B], bert_dur [B,N,768], noise [B,1,256] (device tensors).
         rng (parity mode): 'step_noises' list of [B,1,256], 'sine_noise' [B,L,9], 'har' [B,22,F],
         'F0' / 'N' [B,2T] (teacher-forced prosody curves: the harmonic source integrates F0 into a phase
@@ -52,14 +52,23 @@ class Synthesizer:
         rng = rng or {}
         dev = self.device
         B, N = tokens.shape
+
+        def mark(name):
+            if stage_marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                stage_marks.append((name, ev))
+        mark("start")
         mask = length_to_mask(input_lengths)
         t_en = m.text_encoder(tokens, input_lengths, mask)                       # [B,512,N]
         d_en_rows = m.bert_encoder(bert_dur)                                      # [B,N,512]
+        mark("text_encoder")
         kw = dict(embedding=bert_dur, num_steps=diffusion_steps, embedding_scale=embedding_scale,
                   step_noises=rng.get("step_noises"))
         if self.multispeaker:
             kw["features"] = ref_s
         s_pred = self.sampler(noise, **kw).reshape(B, 256)
+        mark("sampler")
         s = s_pred[:, 128:]
         ref = s_pred[:, :128]
         if self.multispeaker:
@@ -70,6 +79,7 @@ class Synthesizer:
         x, _ = m.predictor.lstm(d)
         logits = m.predictor.duration_proj(x)                                     # [B,N,50]
         pred_dur, dur_f = ops.durations(logits, 0 if self.multispeaker else 5)
+        mark("duration")
         if forced_durations is not None:
             use = forced_durations.to(device=dev, dtype=torch.int32).contiguous()
         elif pin_frames_per_token is not None:
@@ -84,6 +94,7 @@ class Synthesizer:
         en_rows = ops.expand_rows(d, tok)                                         # [B,T,640]
         asr = ops.expand_cl(t_en, tok)                                            # [B,512,T]
         F0, Ncurve = m.predictor.F0Ntrain(en_rows.transpose(-1, -2), s)
+        mark("f0n")
         F0_used = rng["F0"] if "F0" in rng else F0
         N_used = rng["N"] if "N" in rng else Ncurve
         if decoder_events is not None:
@@ -93,6 +104,7 @@ class Synthesizer:
         if decoder_events is not None:
             ev1.record()
             decoder_events.append((ev0, ev1))
+        mark("decoder")
         out = dict(wav=wav, pred_dur=pred_dur, T=T)
         if return_all:
             out.update(t_en=t_en, d_en=d_en_rows.transpose(-1, -2), s_pred=s_pred, s=s, ref=ref, d=d, logits=logits,
