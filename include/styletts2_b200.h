@@ -165,6 +165,15 @@ int st2_linear(const float* A, long long a_bs, long long a_ls, long long a_ks, i
                const float* bias, const float* R, long long ldr, float* C, long long ldc, int M, int Nf, int K,
                int act, void* stream);
 
+/* Tensor-core path of st2_linear for row-layout inputs (A element (m,k) at A + m*lda + k): tcgen05 GEMM with TMEM
+ * accumulators at fp32 accuracy -- operands split into three bf16 planes, six MMAs per product (the integer duration
+ * boundary is downstream of the denoiser).  wtc from st2_linear_tc_weight_layout (st2_linear_tc_weight_bytes bytes),
+ * built from the fp32 weight [Nf,K].  Same call sites as st2_linear. */
+long long st2_linear_tc_weight_bytes(int Nf, int K);
+int st2_linear_tc_weight_layout(const float* w, void* out, int Nf, int K, void* stream);
+int st2_linear_tc(const float* A, long long lda, const void* wtc, const float* bias, const float* R, long long ldr, float* C,
+                  long long ldc, int M, int Nf, int K, int act, void* stream);
+
 /* Multi-head attention without mask (modules.py:523-535): q [B*N, H*D], kv [B*N, 2*H*D]
  * (k | v), out [B*N, H*D]; softmax(q k^T * scale) v per (b,h). D must be 64. */
 int st2_attention(const float* q, const float* kv, float* out, int B, int N, int H, int D, float scale, void* stream);

@@ -1,0 +1,409 @@
+// Tensor-core (tcgen05 / TMEM) GEMM for the row-layout Linears of the style denoiser -- sm_100a.
+//
+//   C[m, n] = act( sum_k A[m,k] * W[n,k] + bias[n] ) + R[m,n]         A,C,R row-major, W = torch Linear weight [Nf,K]
+//
+// fp32-ACCURATE on bf16 tensor cores: the predicted integer durations are downstream of the denoiser, so its
+// arithmetic must stay at fp32 accuracy.  Every operand is split into THREE bf16 planes
+// (x = p0 + p1 + p2, 24 mantissa bits) and every product is evaluated with the six MMAs whose weight is >= 2^-16:
+// p0*q0 + p0*q1 + p1*q0 + p0*q2 + p1*q1 + p2*q0, fp32 accumulation in TMEM (relative error ~2^-23).
+//
+// Mapping (same machinery as conv_tc.cu): D[128 out-features (UMMA M) x 128 tokens (UMMA N)] in TMEM (2 x 128 columns,
+// double buffered).  A operand = weight block [128 n x 16 k], B operand = activation block [128 tokens x 16 k], both
+// K-major no-swizzle "interleave" layout (16-byte rows of 8 bf16).  Weights are pre-split and pre-arranged so that
+// one K-block stage (32 features x 3 planes) is one contiguous 24 KB 1-D TMA bulk copy.  Activations are staged by
+// 8 warps (two threads per token row: 64 contiguous bytes each, software-pipelined one block ahead).  The epilogue
+// needs no transpose: TMEM lane = out-feature, so for each token column the 32 lanes write 32 consecutive floats.
+// Warp roles: warp 0 MMA issue, warp 1 TMA producer, warps 2-9 stagers, warps 10-13 epilogue; persistent CTAs.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace st2 {
+extern long long g_launches;
+
+namespace ltc {
+
+constexpr int TMF = 128;   // out features per tile (UMMA M)
+constexpr int TNT = 128;   // tokens per tile (UMMA N)
+constexpr int KB = 32;     // K block (4 chunks of 8)
+constexpr int NPL = 3;     // bf16 planes per operand
+constexpr int W_STAGES = 4;
+constexpr int W_PLANE_BYTES = 4 * TMF * 16;          // 8 KB
+constexpr int W_STAGE_BYTES = NPL * W_PLANE_BYTES;   // 24 KB
+constexpr int RWP = TNT + 2;                         // chunk pitch in rows (== 2 mod 8: conflict-free 128-bit stores)
+constexpr int A_PLANE_BYTES = 4 * RWP * 16;          // 8320 B
+constexpr int A_BUF_BYTES = NPL * A_PLANE_BYTES;     // 24960 B
+constexpr int A_BUFS = 3;
+constexpr int NUM_STAGERS = 256;
+constexpr int NUM_EPI = 128;
+constexpr int THREADS = 64 + NUM_STAGERS + NUM_EPI;  // 448 (14 warps -> 16-warp allocation, 128 regs)
+constexpr int TMEM_COLS = 512;  // 2 buffers x (hi accumulator 128 cols + lo accumulator 128 cols)
+
+constexpr int SM_W = 0;
+constexpr int SM_A = SM_W + W_STAGES * W_STAGE_BYTES;
+constexpr int SM_BAR = SM_A + A_BUFS * A_BUF_BYTES;
+constexpr int SM_TOTAL = SM_BAR + 256;
+constexpr int B_WFULL = 0, B_WEMPTY = 4, B_AFULL = 8, B_AEMPTY = 11, B_TFULL = 14, B_TEMPTY = 16, B_COUNT = 18;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc() {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // D = F32
+  d |= 1u << 7;                      // A = BF16
+  d |= 1u << 10;                     // B = BF16
+  d |= (uint32_t)(TNT >> 3) << 17;   // N
+  d |= (uint32_t)(TMF >> 4) << 24;   // M
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// x0,x1 -> three packed bf16 pairs (p0, p1, p2) with x = p0 + p1 + p2 to ~2^-24
+__device__ __forceinline__ void split3(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  p0 = pack_bf16(x0, x1);
+  const float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xFFFF0000u);
+  p1 = pack_bf16(r0, r1);
+  const float s0 = r0 - __uint_as_float(p1 << 16), s1 = r1 - __uint_as_float(p1 & 0xFFFF0000u);
+  p2 = pack_bf16(s0, s1);
+}
+
+struct LinArgs {
+  const float* A; long long lda;
+  const uint8_t* wtc;
+  const float* bias;
+  const float* R; long long ldr;
+  float* C; long long ldc;
+  int M, Nf, K, act;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, const int ncb, const int ntiles, const int n_tq) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + SM_BAR;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * B_COUNT);
+  if (tid == 0) {
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
+    for (int i = 0; i < A_BUFS; ++i) { mbar_init(BAR(B_AFULL + i), NUM_STAGERS); mbar_init(BAR(B_AEMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TFULL + i), 1); mbar_init(BAR(B_TEMPTY + i), NUM_EPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc();
+      const uint32_t lbo_a = TMF * 16, lbo_b = RWP * 16;
+      int ws = 0, wph = 0, as = 0, aph = 0, it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(BAR(B_TEMPTY + buf), ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        // Two accumulators per tile: D_hi takes only the leading products p0*q0, D_lo the five correction products
+        // (2^-8 smaller): the tensor core truncates when it adds into an accumulator, so keeping the small terms out of
+        // the big running sum cuts the accumulation error ~6x (measured 4.4e-6 -> fp32-SIMT level at K=1024).
+        const uint32_t d_hi = tmem_base + (uint32_t)buf * (2 * TNT);
+        const uint32_t d_lo = d_hi + TNT;
+        uint32_t first = 1;
+        for (int cb = 0; cb < ncb; ++cb) {
+          mbar_wait(BAR(B_AFULL + as), aph);
+          mbar_wait(BAR(B_WFULL + ws), wph);
+          tc_fence_after();
+          const uint32_t wb = sbase + SM_W + ws * W_STAGE_BYTES;
+          const uint32_t ab = sbase + SM_A + as * A_BUF_BYTES;
+#pragma unroll
+          for (int k16 = 0; k16 < 2; ++k16) {
+            uint64_t da[NPL], db[NPL];
+#pragma unroll
+            for (int p = 0; p < NPL; ++p) {
+              da[p] = make_desc(wb + p * W_PLANE_BYTES + (2 * k16) * lbo_a, lbo_a, 128);
+              db[p] = make_desc(ab + p * A_PLANE_BYTES + (2 * k16) * lbo_b, lbo_b, 128);
+            }
+            tc_mma(d_hi, da[0], db[0], idesc, first ? 0u : 1u);
+            tc_mma(d_lo, da[0], db[1], idesc, first ? 0u : 1u);
+            first = 0;
+            tc_mma(d_lo, da[1], db[0], idesc, 1u);
+            tc_mma(d_lo, da[0], db[2], idesc, 1u);
+            tc_mma(d_lo, da[1], db[1], idesc, 1u);
+            tc_mma(d_lo, da[2], db[0], idesc, 1u);
+          }
+          tc_commit(BAR(B_WEMPTY + ws));
+          tc_commit(BAR(B_AEMPTY + as));
+          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+          if (++as == A_BUFS) { as = 0; aph ^= 1; }
+        }
+        tc_commit(BAR(B_TFULL + buf));
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ weight producer
+    if (lane == 0) {
+      int ws = 0, wph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int cob = tile / n_tq;
+        for (int cb = 0; cb < ncb; ++cb) {
+          mbar_wait(BAR(B_WEMPTY + ws), wph ^ 1);
+          const uint8_t* src = a.wtc + ((size_t)cob * ncb + cb) * W_STAGE_BYTES;
+          mbar_expect_tx(BAR(B_WFULL + ws), W_STAGE_BYTES);
+          bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, W_STAGE_BYTES, BAR(B_WFULL + ws));
+          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 2 + NUM_STAGERS / 32) {
+    // ================================================================ activation stagers
+    // thread -> token row (st >> 1) and half of the 32-feature block (st & 1): 16 contiguous floats = 4 x 128-bit loads;
+    // the loads of block cb+1 are issued before block cb is converted (software pipeline).
+    const int st = tid - 64;
+    const int row = st >> 1, hf = st & 1;
+    const int K_ = a.K, M_ = a.M;
+    int as = 0, aph = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int tq = tile % n_tq;
+      const int m = tq * TNT + row;
+      const bool mok = m < M_;
+      const float* ar = a.A + (long long)(mok ? m : 0) * a.lda + hf * 16;
+      const bool vec_ok = ((a.lda & 3) == 0) && ((reinterpret_cast<size_t>(a.A) & 15) == 0);
+      float4 cur[4], nxt[4];
+      auto load_blk = [&](int cb, float4 (&dst)[4]) {
+        const int k0 = cb * KB + hf * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int k = k0 + 4 * q;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (mok) {
+            if (vec_ok && k + 3 < K_) v = __ldg(reinterpret_cast<const float4*>(ar + cb * KB) + q);
+            else {
+              const float* p = ar + cb * KB + 4 * q;
+              if (k < K_) v.x = __ldg(p);
+              if (k + 1 < K_) v.y = __ldg(p + 1);
+              if (k + 2 < K_) v.z = __ldg(p + 2);
+              if (k + 3 < K_) v.w = __ldg(p + 3);
+            }
+          }
+          dst[q] = v;
+        }
+      };
+      load_blk(0, cur);
+      for (int cb = 0; cb < ncb; ++cb) {
+        if (cb + 1 < ncb) load_blk(cb + 1, nxt);
+        mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
+        uint8_t* base = smem + SM_A + as * A_BUF_BYTES;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {  // two 8-feature chunks of this thread's 16 floats
+          const float4 v0 = cur[2 * c], v1 = cur[2 * c + 1];
+          uint32_t p0[4], p1[4], p2[4];
+          split3(v0.x, v0.y, p0[0], p1[0], p2[0]);
+          split3(v0.z, v0.w, p0[1], p1[1], p2[1]);
+          split3(v1.x, v1.y, p0[2], p1[2], p2[2]);
+          split3(v1.z, v1.w, p0[3], p1[3], p2[3]);
+          const int kc = hf * 2 + c;
+          const size_t off = (size_t)(kc * RWP + row) * 16;
+          *reinterpret_cast<uint4*>(base + off) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+          *reinterpret_cast<uint4*>(base + A_PLANE_BYTES + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+          *reinterpret_cast<uint4*>(base + 2 * A_PLANE_BYTES + off) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+        }
+        fence_proxy_async();
+        mbar_arrive(BAR(B_AFULL + as));
+        if (++as == A_BUFS) { as = 0; aph ^= 1; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
+      }
+    }
+  } else {
+    // ================================================================ epilogue (4 warps; lane = out feature)
+    const int ew = warp & 3;
+    const int M_ = a.M, Nf_ = a.Nf, act_ = a.act;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int cob = tile / n_tq, tq = tile % n_tq;
+      const int buf = it & 1;
+      const int n = cob * TMF + ew * 32 + lane;
+      const bool nok = n < Nf_;
+      const float bias = (a.bias && nok) ? a.bias[n] : 0.f;
+      const int m0 = tq * TNT;
+      mbar_wait(BAR(B_TFULL + buf), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < TNT; c0 += 32) {
+        float v[32];
+        {
+          float vl[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 2 * TNT + c0), v);
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 2 * TNT + TNT + c0), vl);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += vl[j];
+        }
+        float rv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = m0 + c0 + j;
+          rv[j] = (a.R && nok && m < M_) ? a.R[(long long)m * a.ldr + n] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = m0 + c0 + j;
+          float val = v[j] + bias;
+          if (act_ == ST2_ACT_GELU) val = gelu_erf(val);
+          else if (act_ == ST2_ACT_TANH) val = tanhf(val);
+          val += rv[j];
+          if (nok && m < M_) a.C[(long long)m * a.ldc + n] = val;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(B_TEMPTY + buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// W [Nf,K] fp32 -> [n_cob][ncb][3 planes][4 kc][128 n][8 k] bf16
+__global__ void linear_tc_weight_layout_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Nf, int K, int n_cob,
+                                               int ncb) {
+  const long long total = (long long)n_cob * ncb * NPL * 4 * TMF * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int j = (int)(r % 8); r /= 8;
+    const int col = (int)(r % TMF); r /= TMF;
+    const int kc = (int)(r % 4); r /= 4;
+    const int pl = (int)(r % NPL); r /= NPL;
+    const int cb = (int)(r % ncb); r /= ncb;
+    const int cob = (int)r;
+    const int n = cob * TMF + col, k = cb * KB + kc * 8 + j;
+    float v = 0.f;
+    if (n < Nf && k < K) v = w[(long long)n * K + k];
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v);
+    const float r0 = v - __bfloat162float(h0);
+    const __nv_bfloat16 h1 = __float2bfloat16_rn(r0);
+    const __nv_bfloat16 h2 = __float2bfloat16_rn(r0 - __bfloat162float(h1));
+    out[i] = pl == 0 ? h0 : (pl == 1 ? h1 : h2);
+  }
+}
+
+}  // namespace ltc
+}  // namespace st2
+
+using namespace st2;
+
+extern "C" {
+
+long long st2_linear_tc_weight_bytes(int Nf, int K) {
+  return (long long)cdiv(Nf, ltc::TMF) * cdiv(K, ltc::KB) * ltc::W_STAGE_BYTES;
+}
+
+int st2_linear_tc_weight_layout(const float* w, void* out, int Nf, int K, void* stream) {
+  ST2_REQUIRE(w && out && Nf > 0 && K > 0, "st2_linear_tc_weight_layout", "bad args");
+  ltc::linear_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out, Nf, K, cdiv(Nf, ltc::TMF),
+                                                                              cdiv(K, ltc::KB));
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_linear_tc_weight_layout");
+  return 0;
+}
+
+int st2_linear_tc(const float* A, long long lda, const void* wtc, const float* bias, const float* R, long long ldr, float* C,
+                  long long ldc, int M, int Nf, int K, int act, void* stream) {
+  ST2_REQUIRE(A && wtc && C && M > 0 && Nf > 0 && K > 0, "st2_linear_tc", "bad args");
+  ltc::LinArgs a;
+  a.A = A; a.lda = lda; a.wtc = (const uint8_t*)wtc; a.bias = bias; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc;
+  a.M = M; a.Nf = Nf; a.K = K; a.act = act;
+  const int n_tq = cdiv(M, ltc::TNT), n_cob = cdiv(Nf, ltc::TMF), ncb = cdiv(K, ltc::KB);
+  const int ntiles = n_tq * n_cob;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(ltc::linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SM_TOTAL);
+  }
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
+  ltc::linear_tc_kernel<<<grid, ltc::THREADS, ltc::SM_TOTAL, (cudaStream_t)stream>>>(a, ncb, ntiles, n_tq);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_linear_tc");
+  return 0;
+}
+
+}  // extern "C"

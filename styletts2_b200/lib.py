@@ -72,6 +72,9 @@ SIGNATURES = {
     "st2_bcast_cols": [_vp, _ll, _i, _vp, _i, _i, _i, _vp, _vp],
     "st2_mean_rows": [_vp, _ll, _i, _i, _i, _vp, _vp],
     "st2_linear": [_vp, _ll, _ll, _ll, _i, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp],
+    "st2_linear_tc_weight_bytes": [_i, _i],
+    "st2_linear_tc_weight_layout": [_vp, _vp, _i, _i, _vp],
+    "st2_linear_tc": [_vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp],
     "st2_attention": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "st2_lstm_bidir": [_vp, _vp, _vp, _ll, _ll, _ll, _vp, _i, _i, _i, _vp, _vp],
     "st2_kdiff_step": [_vp, _vp, _vp, _f, _f, _f, _f, _vp, _f, _vp, _f, _vp, _i, _vp],
@@ -88,7 +91,7 @@ SIGNATURES = {
     "st2_istft20_expsin": [_vp, _i, _i, _vp, _vp],
 }
 _RESTYPES = {"st2_last_error": C.c_char_p, "st2_launch_count": C.c_longlong, "st2_conv_tc_weight_bytes": C.c_longlong,
-             "st2_convT_tc_weight_bytes": C.c_longlong}
+             "st2_convT_tc_weight_bytes": C.c_longlong, "st2_linear_tc_weight_bytes": C.c_longlong}
 
 _lib = None
 

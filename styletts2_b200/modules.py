@@ -134,10 +134,21 @@ class WNConvTranspose1d(_Cached):
 
 
 class Linear(nn.Linear):
-    """nn.Linear whose forward is the SGEMM kernel."""
+    """nn.Linear whose forward is the GEMM kernel (fp32 SIMT for small row counts, fp32-accurate tcgen05 otherwise)."""
+
+    def _wtc(self):
+        k = (self.weight.data_ptr(), self.weight._version, str(self.weight.device))
+        c = self.__dict__.get("_wtc_cache")
+        if c is None or c[0] != k:
+            with torch.no_grad():
+                c = (k, ops.linear_tc_weight_layout(self.weight))
+            self.__dict__["_wtc_cache"] = c
+        return c[1]
 
     def forward(self, x, act=ACT_NONE, R=None, out=None):
-        return ops.linear(x, self.weight, self.bias, act=act, R=R, out=out)
+        rows = x.numel() // x.shape[-1]
+        wtc = self._wtc() if (ops.USE_TC and rows >= ops.LINEAR_TC_MIN_ROWS and x.is_cuda) else None
+        return ops.linear(x, self.weight, self.bias, act=act, R=R, out=out, wtc=wtc)
 
 
 class LinearNorm(nn.Module):

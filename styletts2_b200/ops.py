@@ -249,8 +249,21 @@ def _rows_view(t):
     return t, t.numel() // K, K
 
 
-def linear(A, W, bias=None, *, act=ACT_NONE, R=None, out=None):
-    """A [..., K] @ W[Nf,K]^T (+bias, act, +R) -> [..., Nf].  Rows may be strided (ld)."""
+LINEAR_TC_MIN_ROWS = 256
+
+
+def linear_tc_weight_layout(W: torch.Tensor) -> torch.Tensor:
+    """fp32 Linear weight [Nf,K] -> three-plane bf16 tensor-core blocks (opaque uint8 buffer)"""
+    W = W.detach().contiguous()
+    nf, k = W.shape
+    out = torch.empty(int(L.load().st2_linear_tc_weight_bytes(nf, k)), dtype=torch.uint8, device=W.device)
+    L.call("st2_linear_tc_weight_layout", ptr(W), ptr(out), nf, k, stream_ptr())
+    return out
+
+
+def linear(A, W, bias=None, *, act=ACT_NONE, R=None, out=None, wtc=None):
+    """A [..., K] @ W[Nf,K]^T (+bias, act, +R) -> [..., Nf].  Rows may be strided (ld).
+    wtc: optional tensor-core weight blocks (linear_tc_weight_layout) -> fp32-accurate tcgen05 path for big M."""
     K = A.shape[-1]
     A2, M, lda = _rows_view(A)
     Nf = W.shape[0]
@@ -263,7 +276,10 @@ def linear(A, W, bias=None, *, act=ACT_NONE, R=None, out=None):
     if R is not None:
         R2, Mr, ldr = _rows_view(R)
         assert R2.data_ptr() == R.data_ptr() and Mr == M
-    L.call("st2_linear", ptr(A2), 0, lda, 1, M, ptr(W), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
+    if wtc is not None and USE_TC and M >= LINEAR_TC_MIN_ROWS:
+        L.call("st2_linear_tc", ptr(A2), lda, ptr(wtc), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
+    else:
+        L.call("st2_linear", ptr(A2), 0, lda, 1, M, ptr(W), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
     return out
 
 

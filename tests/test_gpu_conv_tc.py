@@ -101,3 +101,20 @@ def test_conv_transpose1d_tc_matches_fp32(cfg):
     ca, cb = ops.adain_coef(st, torch.zeros(2, 2 * Cout, device=D))
     ea = 1 / torch.sqrt(ref.var(-1, unbiased=False) + 1e-5)
     assert maxdiff(ca, ea) / float(ea.abs().max()) < 1e-4 and maxdiff(cb, -ref.mean(-1) * ea) < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(300, 1024, 512), (4096, 1024, 2048), (1000, 257, 1024), (260, 2048, 1024), (512, 512, 50)])
+def test_linear_tc_fp32_accurate(shape):
+    """3-plane bf16 split, 6 MMAs: must be at fp32 accuracy (duration boundary downstream): 2e-6 relative."""
+    from styletts2_b200 import ops
+    from styletts2_b200.lib import ACT_GELU
+    M, K, Nf = shape
+    A, W, b, R = rnd(M, K, seed=1), rnd(Nf, K, seed=2, scale=1 / math.sqrt(K)), rnd(Nf, seed=3), rnd(M, Nf, seed=4)
+    ref = (F.gelu(F.linear(A.double(), W.double(), b.double())) + R.double()).float()
+    Wd = W.to(D)
+    y = ops.linear(A.to(D), Wd, b.to(D), act=ACT_GELU, R=R.to(D), wtc=ops.linear_tc_weight_layout(Wd))
+    y32 = ops.linear(A.to(D), Wd, b.to(D), act=ACT_GELU, R=R.to(D))
+    e_tc = maxdiff(y, ref) / float(ref.abs().max())
+    e_32 = maxdiff(y32, ref) / float(ref.abs().max())
+    record("linear_tc", shape=str(shape), rel_err_tc=e_tc, rel_err_fp32_simt=e_32)
+    assert e_tc < 2e-6, (e_tc, e_32)
