@@ -299,32 +299,43 @@ __global__ void instance_stats_kernel(const float* __restrict__ x, long long bst
   }
 }
 
-// Merge partials (Chan et al.) in fp64, fixed order; biased variance; AdaIN coefficients.
+// Merge partials (Chan et al.) in fp64; biased variance; AdaIN coefficients.  One WARP per (b,c): lanes take every
+// 32nd partial (coalesced 12-byte records), then a fixed shuffle tree merges the 32 lane results (deterministic).
+__device__ __forceinline__ void chan_merge(double& n, double& mean, double& m2, double nb, double mb, double m2b) {
+  if (nb <= 0.0) return;
+  const double nn = n + nb;
+  const double delta = mb - mean;
+  mean += delta * (nb / nn);
+  m2 += m2b + delta * delta * (n * nb / nn);
+  n = nn;
+}
+
 __global__ void adain_coef_kernel(const float* __restrict__ stats, int nparts, const float* __restrict__ gb,
                                   long long gb_stride, int B, int C, float eps, float* __restrict__ a,
                                   float* __restrict__ bo) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C;
   const float* sp = stats + (long long)i * nparts * 3;
   double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    const double nb = sp[p * 3 + 0];
-    if (nb <= 0.0) continue;
-    const double mb = sp[p * 3 + 1], m2b = sp[p * 3 + 2];
-    const double nn = n + nb;
-    const double delta = mb - mean;
-    mean += delta * (nb / nn);
-    m2 += m2b + delta * delta * (n * nb / nn);
-    n = nn;
+  for (int p = lane; p < nparts; p += 32) chan_merge(n, mean, m2, sp[p * 3 + 0], sp[p * 3 + 1], sp[p * 3 + 2]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double nb = __shfl_down_sync(0xffffffffu, n, o);
+    const double mb = __shfl_down_sync(0xffffffffu, mean, o);
+    const double m2b = __shfl_down_sync(0xffffffffu, m2, o);
+    chan_merge(n, mean, m2, nb, mb, m2b);
   }
-  const double var = m2 / n;
-  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float gamma = gb[(long long)b * gb_stride + c];
-  const float beta = gb[(long long)b * gb_stride + C + c];
-  const float av = (1.0f + gamma) * rstd;
-  a[i] = av;
-  bo[i] = beta - (float)mean * av;
+  if (lane == 0) {
+    const double var = m2 / n;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float gamma = gb[(long long)b * gb_stride + c];
+    const float beta = gb[(long long)b * gb_stride + C + c];
+    const float av = (1.0f + gamma) * rstd;
+    a[i] = av;
+    bo[i] = beta - (float)mean * av;
+  }
 }
 
 // AdaIN -> LeakyReLU -> depthwise ConvTranspose1d(k3,s2,p1,op1): y[2i] = w1*z[i] + pb,
@@ -467,7 +478,7 @@ int st2_instance_stats(const float* x, long long bstride, int B, int C, int L, f
 int st2_adain_coef(const float* stats, int nparts, const float* gb, long long gb_stride, int B, int C, float eps,
                    float* a, float* b, void* stream) {
   ST2_REQUIRE(stats && gb && a && b && nparts > 0 && B > 0 && C > 0, "st2_adain_coef", "bad args");
-  adain_coef_kernel<<<cdiv(B * C, 128), 128, 0, (cudaStream_t)stream>>>(stats, nparts, gb, gb_stride, B, C, eps, a, b);
+  adain_coef_kernel<<<cdiv(B * C, 8), 256, 0, (cudaStream_t)stream>>>(stats, nparts, gb, gb_stride, B, C, eps, a, b);
   ++g_launches;
   ST2_CHECK_LAUNCH("st2_adain_coef");
   return 0;

@@ -193,12 +193,19 @@ class LSTM(_Cached):
         wih = torch.cat([self.weight_ih_l0, self.weight_ih_l0_reverse], 0).contiguous()
         bias = torch.cat([self.bias_ih_l0 + self.bias_hh_l0, self.bias_ih_l0_reverse + self.bias_hh_l0_reverse], 0).contiguous()
         whh = torch.stack([self.weight_hh_l0, self.weight_hh_l0_reverse], 0).contiguous()
-        return wih, bias, whh
+        wtc = ops.linear_tc_weight_layout(wih) if (ops.USE_TC and wih.is_cuda) else None
+        return wih, bias, whh, wtc
 
     def run(self, x, B, Lr, strides, out, out_strides, lengths=None):
         """x element (b,l,k) at strides (bs,ls,ks); out element (b,t,c) at out_strides."""
-        wih, bias, whh = self.prepared()
-        gx = ops.linear_strided(x, B, Lr, self.input_size, strides[0], strides[1], strides[2], wih, bias)
+        wih, bias, whh, wtc = self.prepared()
+        if wtc is not None and strides[2] == 1 and strides[0] == Lr * strides[1] and B * Lr >= ops.LINEAR_TC_MIN_ROWS:
+            # row-layout input: input projection on the fp32-accurate tensor-core GEMM
+            gx = ops.empty(B * Lr, wih.shape[0], device=x.device)
+            ops.L.call("st2_linear_tc", ops.ptr(x), strides[1], ops.ptr(wtc), ops.ptr(bias), None, 0, ops.ptr(gx), gx.stride(0),
+                       B * Lr, wih.shape[0], self.input_size, 0, ops.stream_ptr())
+        else:
+            gx = ops.linear_strided(x, B, Lr, self.input_size, strides[0], strides[1], strides[2], wih, bias)
         ops.lstm_bidir(gx, whh, out, out_strides[0], out_strides[1], out_strides[2], B, Lr, self.hidden_size, lengths)
         return out
 
