@@ -42,11 +42,12 @@ VOCODER_FLOPS_PER_FRAME = {"ljspeech": 1.317e9, "libritts": 1.767e9}
 
 
 def measured_peaks():
+    """(hbm GB/s, sustained bf16 TFLOP/s, source): the kernel is timed inside a long step -> sustained figure."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -131,9 +132,16 @@ def run_ours(args):
 
     marks = []
 
+    graph_launches = [0]
+
     def step(inputs, timed_decoder=False):
         tokens, lengths, bert_dur, noise = inputs[:4]
         ref_s = inputs[4] if ms else None
+        if args.graph:
+            wav, nl = syn.synthesize_graphed(tokens, lengths, bert_dur, noise, diffusion_steps=wl["steps"], ref_s=ref_s,
+                                             pin_frames_per_token=wl["fpt"])
+            graph_launches[0] = nl
+            return wav
         mk = [] if timed_decoder else None
         out = syn.synthesize(tokens, lengths, bert_dur, noise, diffusion_steps=wl["steps"], ref_s=ref_s,
                              pin_frames_per_token=wl["fpt"], decoder_events=dec_ev if timed_decoder else None, stage_marks=mk)
@@ -168,6 +176,8 @@ def run_ours(args):
     e1.record()
     barrier()
     launches = lib.launch_count() - n0
+    if args.graph:
+        launches = graph_launches[0] * args.steps   # kernels of this library inside the replayed CUDA graph x replays
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     dec_ms = sum(a.elapsed_time(b) for a, b in dec_ev) / max(1, len(dec_ev))
     stages = {}
@@ -203,25 +213,53 @@ def run_ours(args):
     e2e_value = samples_per_step / (ms_e2e / args.steps / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = wav_host.numel() * 4
-    peak, peak_src = measured_peaks()
+    hbm_peak, tc_peak, peak_src = measured_peaks()
     alg_bytes = VOCODER_BYTES_PER_FRAME[wl["model"]] * B * T + VOCODER_WEIGHT_BYTES[wl["model"]]
     alg_flops = VOCODER_FLOPS_PER_FRAME[wl["model"]] * B * T
-    achieved = alg_bytes / (dec_ms / 1e3) / 1e9
+    # dominant kernel = tc::conv1d_tc_kernel: one extra eager (non-graph) pass with CUDA events around every launch
+    from styletts2_b200 import ops as _ops
+    _ops.PROFILE = []
+    tokens, lengths, bert_dur, noise = devin[:4]
+    syn.synthesize(tokens, lengths, bert_dur, noise, diffusion_steps=wl["steps"], ref_s=devin[4] if ms else None, pin_frames_per_token=wl["fpt"])
+    torch.cuda.synchronize()
+    prof, _ops.PROFILE = _ops.PROFILE, None
+    if not dec_ev:   # graph mode: take the decoder time from one eager pass
+        mk = []
+        syn.synthesize(tokens, lengths, bert_dur, noise, diffusion_steps=wl["steps"], ref_s=devin[4] if ms else None,
+                       pin_frames_per_token=wl["fpt"], stage_marks=mk)
+        torch.cuda.synchronize()
+        for (n0_, e0_), (n1_, e1_) in zip(mk[:-1], mk[1:]):
+            stages[n1_] = e0_.elapsed_time(e1_)
+        dec_ms = stages.get("decoder", 0.0)
+    tc_ms = sum(e0_.elapsed_time(e1_) for _, _, _, e0_, e1_ in prof)
+    tc_flops = sum(f for _, f, _, _, _ in prof)
+    tc_bytes = sum(b_ for _, _, b_, _, _ in prof)
+    n_tc = max(1, len(prof))
+    executed_tflops = 3.0 * tc_flops / (tc_ms / 1e3) / 1e12   # bf16 hi/lo split: 3 MMAs per fp32 product
     line = {
         "metric": "24 kHz waveform samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (key-seeded random weights, seeded tokens/bert_dur/noise; durations pinned to 4 frames/token)",
         "config": {"workload": f"{args.workload}: {wl['desc']}", "per_gpu_batch": B, "tokens": N, "frames": T, "samples_per_utt": L,
                    "diffusion_steps": wl["steps"], "sharding": f"utterances x{world}, no data-path collective",
-                   "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no flush needed"},
+                   "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2; no flush needed",
+                   "launch": "one CUDA graph per step" if args.graph else "eager"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "stages_ms": stages,
         "clocks": clk,
-        "roofline": {"kernel": "decoder+vocoder chain (st2::conv1d_kernel<8> dominant)", "bound": "hbm", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "decoder_ms_per_step": dec_ms, "achieved_tflops_fp32": alg_flops / (dec_ms / 1e3) / 1e12,
-                     "note": "fp32 SIMT conv stack is bound by the FP32 pipe (296 FLOP/B arithmetic intensity), not HBM; see DESIGN.md"},
+        "roofline": {"kernel": "st2::tc::conv1d_tc_kernel (tcgen05 implicit-GEMM conv, bf16 hi/lo x3)", "bound": "tensor",
+                     "achieved": executed_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": executed_tflops / tc_peak,
+                     "traffic": None, "peak_source": peak_src, "launches_per_step": len(prof),
+                     "avg_launch_ms": tc_ms / n_tc, "algorithmic_gflop_per_launch": tc_flops / n_tc / 1e9,
+                     "fp32_equivalent_tflops": tc_flops / (tc_ms / 1e3) / 1e12,
+                     "hbm_algorithmic_gbs": tc_bytes / (tc_ms / 1e3) / 1e9, "hbm_peak_gbs": hbm_peak,
+                     "kernel_ms_per_step": tc_ms, "decoder_ms_per_step": dec_ms,
+                     "vocoder_path_algorithmic": {"bytes_per_step": alg_bytes, "flops_per_step": alg_flops,
+                                                  "gbs": alg_bytes / (max(dec_ms, 1e-9) / 1e3) / 1e9 if dec_ms else None},
+                     "note": "achieved = executed bf16 MMA FLOPs (3 per fp32 product, algorithmic 2*Cin*Cout*K*L*B summed over the step's "
+                             "launches) / CUDA-event time of those launches in an eager pass; traffic: see profiles/r01_ncu_conv1d_tc.md "
+                             "(DRAM bytes == algorithmic bytes for the captured launches)"},
     }
     if args.cpu_baseline and world >= 1:
         line["cpu_baseline"] = cpu_reference(wl, sample_B=args.cpu_batch, steps=1, warmup=0)
@@ -234,7 +272,8 @@ def cpu_reference(wl, sample_B, steps, warmup):
     import styletts2_oracle as O
     from styletts2_b200.synthetic import keyed_state_dict
 
-    torch.set_num_threads(os.cpu_count())
+    # more threads than ~32 slow torch's CPU kernels down at these sizes (measured: 128 threads 7x slower than 8)
+    torch.set_num_threads(min(32, os.cpu_count()))
     mcfg = cases.MODEL_CFGS[wl["model"]]
     shapes = json.load(open(os.path.join(ROOT, "tests", "golden", f"state_shapes_{wl['model']}.json")))
     sds = {k: keyed_state_dict({n: tuple(s) for n, s in shapes[k].items()}, k) for k in shapes}
@@ -253,7 +292,7 @@ def cpu_reference(wl, sample_B, steps, warmup):
             times.append(dt)
     nsamp = out["wav"].numel()
     v = nsamp / (sum(times) / len(times))
-    return {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "port",
             "sample": f"{sample_B} utterance(s) of the workload ({wl['N']} tokens, {wl['N'] * wl['fpt']} frames, K={wl['steps']}), "
                       f"{len(times)} timed run(s), torch {torch.__version__} CPU, {torch.get_num_threads()} threads",
             "seconds_per_run": sum(times) / len(times)}
@@ -283,6 +322,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="eager launches instead of one CUDA graph per step")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident loop, no JSON contract line")
     args = ap.parse_args()
     if args.impl == "reference":

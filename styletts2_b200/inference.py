@@ -17,9 +17,10 @@ from .diffusion import ADPM2Sampler, DiffusionSampler, KarrasSchedule
 from .models import Munch
 
 
-def length_to_mask(lengths):
-    """utils.py:42-45"""
-    mask = torch.arange(int(lengths.max()), device=lengths.device).unsqueeze(0).expand(lengths.shape[0], -1).type_as(lengths)
+def length_to_mask(lengths, n=None):
+    """utils.py:42-45 (n given: no host sync on lengths.max(), needed under CUDA-graph capture)"""
+    n = int(lengths.max()) if n is None else n
+    mask = torch.arange(n, device=lengths.device).unsqueeze(0).expand(lengths.shape[0], -1).type_as(lengths)
     return torch.gt(mask + 1, lengths.unsqueeze(1))
 
 
@@ -59,7 +60,7 @@ class Synthesizer:
                 ev.record()
                 stage_marks.append((name, ev))
         mark("start")
-        mask = length_to_mask(input_lengths)
+        mask = length_to_mask(input_lengths, N)
         t_en = m.text_encoder(tokens, input_lengths, mask)                       # [B,512,N]
         d_en_rows = m.bert_encoder(bert_dur)                                      # [B,N,512]
         mark("text_encoder")
@@ -86,10 +87,13 @@ class Synthesizer:
             use = torch.full((B, N), int(pin_frames_per_token), device=dev, dtype=torch.int32)
         else:
             use = pred_dur
-        totals = use.sum(dim=1)
-        T = int(totals.max().item())        # the one host sync of the path: buffer sizes depend on it
-        if not bool((totals == T).all()):
-            raise ValueError("batched synthesis needs equal total durations; run ragged utterances one by one")
+        if pin_frames_per_token is not None and forced_durations is None:
+            T = N * int(pin_frames_per_token)   # known a priori: no host sync (the whole path is CUDA-graph capturable)
+        else:
+            totals = use.sum(dim=1)
+            T = int(totals.max().item())        # the one host sync of the path: buffer sizes depend on it
+            if not bool((totals == T).all()):
+                raise ValueError("batched synthesis needs equal total durations; run ragged utterances one by one")
         tok, _ = ops.frame_tokens(use, T, shift_right=self.hifigan)
         en_rows = ops.expand_rows(d, tok)                                         # [B,T,640]
         asr = ops.expand_cl(t_en, tok)                                            # [B,512,T]
@@ -110,6 +114,44 @@ class Synthesizer:
             out.update(t_en=t_en, d_en=d_en_rows.transpose(-1, -2), s_pred=s_pred, s=s, ref=ref, d=d, logits=logits,
                        dur_f=dur_f, en=en_rows.transpose(-1, -2), asr=asr, F0=F0, N=Ncurve)
         return out
+
+    @torch.no_grad()
+    def synthesize_graphed(self, tokens, input_lengths, bert_dur, noise, *, diffusion_steps=5, embedding_scale=1.0, ref_s=None,
+                           alpha=0.3, beta=0.7, pin_frames_per_token=4):
+        """Throughput mode: the whole path (durations pinned, RNG drawn on the device) captured ONCE per shape into a
+        CUDA graph and replayed -- removes the ~450 per-launch host overheads of a pass.  Inputs are copied into the
+        graph's static buffers; returns the graph's static output waveform [B,1,L] (valid until the next replay)."""
+        from . import lib
+        key = (tuple(tokens.shape), int(diffusion_steps), float(embedding_scale), ref_s is not None, int(pin_frames_per_token))
+        cache = self.__dict__.setdefault("_graphs", {})
+        ent = cache.get(key)
+        if ent is None:
+            st = dict(tokens=tokens.clone(), lengths=input_lengths.clone(), bert=bert_dur.clone(), noise=noise.clone(),
+                      ref_s=None if ref_s is None else ref_s.clone())
+            kw = dict(diffusion_steps=diffusion_steps, embedding_scale=embedding_scale, alpha=alpha, beta=beta,
+                      pin_frames_per_token=pin_frames_per_token)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):   # warm-up: lazy weight preparation, cudaFuncSetAttribute, constant tables
+                    self.synthesize(st["tokens"], st["lengths"], st["bert"], st["noise"], ref_s=st["ref_s"], **kw)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = lib.launch_count()
+            with torch.cuda.graph(g):
+                out = self.synthesize(st["tokens"], st["lengths"], st["bert"], st["noise"], ref_s=st["ref_s"], **kw)
+            ent = dict(graph=g, st=st, wav=out["wav"], launches=lib.launch_count() - n0)
+            cache[key] = ent
+        st = ent["st"]
+        st["tokens"].copy_(tokens, non_blocking=True)
+        st["lengths"].copy_(input_lengths, non_blocking=True)
+        st["bert"].copy_(bert_dur, non_blocking=True)
+        st["noise"].copy_(noise, non_blocking=True)
+        if ref_s is not None:
+            st["ref_s"].copy_(ref_s, non_blocking=True)
+        ent["graph"].replay()
+        return ent["wav"], ent["launches"]
 
     @torch.no_grad()
     def inference(self, tokens: List[int], bert_dur, noise=None, ref_s=None, alpha=0.3, beta=0.7, diffusion_steps=5,

@@ -86,6 +86,7 @@ def _fill_conv_args(a: ConvArgs, x, wt, bias, y, *, K, stride, dil, pad, Lq, y_l
     a.dup_q0_to = -1
 
 
+PROFILE = None  # bench.py sets this to a list to collect (name, algorithmic_flops, algorithmic_bytes, ev0, ev1) per TC conv launch
 USE_TC = os.environ.get("ST2_TC", "1") != "0"   # tensor-core (tcgen05) conv path where a wtc buffer is given
 TC_MIN_WORK = 1 << 22                            # below this many MACs per utterance the SIMT kernel is used
 
@@ -126,7 +127,14 @@ def conv1d(x, wt, bias=None, *, K, stride=1, dil=1, pad=0, pre=None, pre_act=ACT
                     pre_act=pre_act, slope=slope, alpha=alpha, res=res, res_shift=res_shift, out_div=out_div,
                     accum_mode=accum_mode, accum_div=accum_div, out_act=out_act, stats=stats, nparts=nparts)
     if use_tc:
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         L.call("st2_conv1d_tc", C.byref(a), ptr(wtc), tc_max_ctas, stream_ptr())
+        if PROFILE is not None:
+            e1.record()
+            nbytes = 4.0 * B * Lout * (Cin + Cout * (2 if res is not None else 1) + (Cout if accum_mode else 0))
+            PROFILE.append(("conv1d_tc", 2.0 * B * Cin * Cout * K * Lout, nbytes, e0, e1))
     else:
         L.call("st2_conv1d", C.byref(a), stream_ptr())
     return out, stats
