@@ -207,6 +207,8 @@ def run_ours(args):
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     clk = clocks.stop() if rank == 0 else None
     if rank != 0:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
         return
     ms_per_step = ms_total / args.steps
     value = samples_per_step / (ms_per_step / 1e3)
@@ -264,6 +266,9 @@ def run_ours(args):
     if args.cpu_baseline and world >= 1:
         line["cpu_baseline"] = cpu_reference(wl, sample_B=args.cpu_batch, steps=1, warmup=0)
     print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 def cpu_reference(wl, sample_B, steps, warmup):

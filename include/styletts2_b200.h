@@ -30,6 +30,7 @@ extern "C" {
 #define ST2_ACT_SNAKE 2 /* x + sin(alpha x)^2 / alpha, alpha per channel */
 #define ST2_ACT_TANH 3
 #define ST2_ACT_GELU 4 /* exact erf GELU (nn.GELU default) */
+#define ST2_ACT_GELU_TANH 5 /* "gelu_new" tanh approximation (transformers AlbertConfig.hidden_act, PL-BERT) */
 
 const char* st2_last_error(void);
 int st2_abi_version(void);
@@ -177,6 +178,14 @@ int st2_linear_tc(const float* A, long long lda, const void* wtc, const float* b
 /* Multi-head attention without mask (modules.py:523-535): q [B*N, H*D], kv [B*N, 2*H*D]
  * (k | v), out [B*N, H*D]; softmax(q k^T * scale) v per (b,h). D must be 64. */
 int st2_attention(const float* q, const float* kv, float* out, int B, int N, int H, int D, float scale, void* stream);
+/* General form: q rows at q + m*q_ld, k / v rows at k|v + m*kv_ld, out rows at out + m*out_ld (head h in columns
+ * h*D..); lengths (int32 [B]) or NULL = key-padding mask (keys n >= lengths[b] excluded), as the additive -inf
+ * attention mask of transformers.AlbertModel (PL-BERT, Utils/PLBERT/util.py:6-12). */
+int st2_attention_ex(const float* q, long long q_ld, const float* k, const float* v, long long kv_ld, float* out, long long out_ld,
+                     const int* lengths, int B, int N, int H, int D, float scale, void* stream);
+/* ALBERT embeddings: out[(b,n), :] = word[tokens[b,n]] + pos[n] + type0   (E columns) */
+int st2_embedding_sum_rows(const long long* tokens, const float* word, const float* pos, const float* type0, int B, int N, int E,
+                           float* out, void* stream);
 
 /* Bidirectional single-layer LSTM recurrence (models.py:300,450,453,523; gate order i,f,g,o).
  * gx [B*L, 8H] = x W_ih^T + b_ih + b_hh for (fwd | bwd); whh [2][4H][H]; out element

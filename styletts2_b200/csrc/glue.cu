@@ -22,6 +22,16 @@ __global__ void embedding_cl_kernel(const long long* __restrict__ tokens, const 
   out[((long long)b * C + c) * N + n] = masked ? 0.f : table[tok * C + c];
 }
 
+__global__ void embedding_sum_rows_kernel(const long long* __restrict__ tokens, const float* __restrict__ word,
+                                          const float* __restrict__ pos, const float* __restrict__ type0, int N, int E,
+                                          float* __restrict__ out) {
+  const int row = blockIdx.x;  // (b,n)
+  const int n = row % N;
+  const long long tok = tokens[row];
+  for (int e = threadIdx.x; e < E; e += blockDim.x)
+    out[(long long)row * E + e] = __fadd_rn(__fadd_rn(word[tok * E + e], type0[e]), pos[(long long)n * E + e]);
+}
+
 __global__ void durations_kernel(const float* __restrict__ logits, int rows, int N, int J, int last_plus,
                                  int* __restrict__ pred, float* __restrict__ dur_f) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,6 +158,15 @@ int st2_embedding_cl(const long long* tokens, const float* table, const int* len
   embedding_cl_kernel<<<dim3(cdiv(N, 128), C, B), 128, 0, (cudaStream_t)stream>>>(tokens, table, lengths, N, C, out);
   ++g_launches;
   ST2_CHECK_LAUNCH("st2_embedding_cl");
+  return 0;
+}
+
+int st2_embedding_sum_rows(const long long* tokens, const float* word, const float* pos, const float* type0, int B, int N, int E,
+                           float* out, void* stream) {
+  ST2_REQUIRE(tokens && word && pos && type0 && out && B > 0 && N > 0 && E > 0, "st2_embedding_sum_rows", "bad args");
+  embedding_sum_rows_kernel<<<B * N, 128, 0, (cudaStream_t)stream>>>(tokens, word, pos, type0, N, E, out);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_embedding_sum_rows");
   return 0;
 }
 

@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
           float val = v[j] + bias;
           if (act_ == ST2_ACT_GELU) val = gelu_erf(val);
           else if (act_ == ST2_ACT_TANH) val = tanhf(val);
+          else if (act_ == ST2_ACT_GELU_TANH) val = gelu_tanh(val);
           val += rv[j];
           if (nok && m < M_) a.C[(long long)m * a.ldc + n] = val;
         }

@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A
       float v = acc[i][j] + (bias ? bias[n] : 0.f);
       if (act == ST2_ACT_GELU) v = gelu_erf(v);
       else if (act == ST2_ACT_TANH) v = tanhf(v);
+      else if (act == ST2_ACT_GELU_TANH) v = gelu_tanh(v);
       if (R) v += R[(long long)m * ldr + n];
       C[(long long)m * ldc + n] = v;
     }
@@ -156,8 +157,9 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A
 // 32 through shared memory; lane-per-key dot products, online softmax, P V through shared memory.
 constexpr int ATT_D = 64, ATT_QW = 4, ATT_WARPS = 4, ATT_KC = 32;
 
-__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ q, const float* __restrict__ kv,
-                                                        float* __restrict__ out, int N, int H, float scale) {
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ q, long long q_ld, const float* __restrict__ kp,
+                                                        const float* __restrict__ vp, long long kv_ld, float* __restrict__ out,
+                                                        long long out_ld, const int* __restrict__ lengths, int N, int H, float scale) {
   __shared__ __align__(16) float Qs[ATT_WARPS * ATT_QW][ATT_D];
   __shared__ __align__(16) float Ks[ATT_KC][ATT_D + 4];
   __shared__ __align__(16) float Vs[ATT_KC][ATT_D];
@@ -165,23 +167,23 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
   const int q0 = blockIdx.x * (ATT_WARPS * ATT_QW);
-  const int HD = H * ATT_D;
+  const int NK = lengths ? min(N, lengths[b]) : N;  // keys beyond the utterance length are masked out
   for (int i = tid; i < ATT_WARPS * ATT_QW * ATT_D; i += 128) {
     const int qi = i / ATT_D, d = i - qi * ATT_D;
     const int n = q0 + qi;
-    Qs[qi][d] = n < N ? q[((long long)b * N + n) * HD + h * ATT_D + d] : 0.f;
+    Qs[qi][d] = n < N ? q[((long long)b * N + n) * q_ld + h * ATT_D + d] : 0.f;
   }
   float m[ATT_QW], l[ATT_QW], o0[ATT_QW], o1[ATT_QW];
 #pragma unroll
   for (int i = 0; i < ATT_QW; ++i) { m[i] = -INFINITY; l[i] = 0.f; o0[i] = 0.f; o1[i] = 0.f; }
-  for (int k0 = 0; k0 < N; k0 += ATT_KC) {
+  for (int k0 = 0; k0 < NK; k0 += ATT_KC) {
     __syncthreads();
     for (int i = tid; i < ATT_KC * ATT_D; i += 128) {
       const int kj = i / ATT_D, d = i - kj * ATT_D;
       const int n = k0 + kj;
-      const long long base = ((long long)b * N + n) * (2 * HD) + h * ATT_D + d;
-      Ks[kj][d] = n < N ? kv[base] : 0.f;
-      Vs[kj][d] = n < N ? kv[base + HD] : 0.f;
+      const long long base = ((long long)b * N + n) * kv_ld + h * ATT_D + d;
+      Ks[kj][d] = n < NK ? kp[base] : 0.f;
+      Vs[kj][d] = n < NK ? vp[base] : 0.f;
     }
     __syncthreads();
     float s[ATT_QW];
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
         s[i] = fmaf(qq.w, kk.w, s[i]);
       }
     }
-    const bool kvalid = (k0 + lane) < N;
+    const bool kvalid = (k0 + lane) < NK;
 #pragma unroll
     for (int i = 0; i < ATT_QW; ++i) {
       const float sv = kvalid ? s[i] * scale : -INFINITY;
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
     if (n < N) {
       const float inv = 1.0f / l[i];
       float2 r = make_float2(o0[i] * inv, o1[i] * inv);
-      *reinterpret_cast<float2*>(&out[((long long)b * N + n) * HD + h * ATT_D + 2 * lane]) = r;
+      *reinterpret_cast<float2*>(&out[((long long)b * N + n) * out_ld + h * ATT_D + 2 * lane]) = r;
     }
   }
 }
@@ -280,14 +282,22 @@ int st2_linear(const float* A, long long a_bs, long long a_ls, long long a_ks, i
   return 0;
 }
 
-int st2_attention(const float* q, const float* kv, float* out, int B, int N, int H, int D, float scale, void* stream) {
-  ST2_REQUIRE(q && kv && out && B > 0 && N > 0 && H > 0, "st2_attention", "bad args");
-  ST2_REQUIRE(D == ATT_D, "st2_attention", "head_features must be 64");
+int st2_attention_ex(const float* q, long long q_ld, const float* k, const float* v, long long kv_ld, float* out, long long out_ld,
+                     const int* lengths, int B, int N, int H, int D, float scale, void* stream) {
+  ST2_REQUIRE(q && k && v && out && B > 0 && N > 0 && H > 0, "st2_attention_ex", "bad args");
+  ST2_REQUIRE(D == ATT_D, "st2_attention_ex", "head_features must be 64");
+  ST2_REQUIRE((out_ld & 1) == 0, "st2_attention_ex", "out_ld must be even");
   dim3 grid(cdiv(N, ATT_WARPS * ATT_QW), B * H);
-  attention_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(q, kv, out, N, H, scale);
+  attention_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(q, q_ld, k, v, kv_ld, out, out_ld, lengths, N, H, scale);
   ++g_launches;
-  ST2_CHECK_LAUNCH("st2_attention");
+  ST2_CHECK_LAUNCH("st2_attention_ex");
   return 0;
+}
+
+int st2_attention(const float* q, const float* kv, float* out, int B, int N, int H, int D, float scale, void* stream) {
+  ST2_REQUIRE(q && kv, "st2_attention", "bad args");
+  const long long HD = (long long)H * D;
+  return st2_attention_ex(q, HD, kv, kv + HD, 2 * HD, out, HD, nullptr, B, N, H, D, scale, stream);
 }
 
 }  // extern "C"

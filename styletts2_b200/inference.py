@@ -61,6 +61,8 @@ class Synthesizer:
                 stage_marks.append((name, ev))
         mark("start")
         mask = length_to_mask(input_lengths, N)
+        if bert_dur is None:   # PL-BERT on our kernels (styletts2_b200.plbert.PLBert passed to build_model)
+            bert_dur = m.bert(tokens, attention_mask=(~mask).int())
         t_en = m.text_encoder(tokens, input_lengths, mask)                       # [B,512,N]
         d_en_rows = m.bert_encoder(bert_dur)                                      # [B,N,512]
         mark("text_encoder")

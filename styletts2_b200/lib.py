@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstyletts2_b200.so")
 
-ACT_NONE, ACT_LRELU, ACT_SNAKE, ACT_TANH, ACT_GELU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_LRELU, ACT_SNAKE, ACT_TANH, ACT_GELU, ACT_GELU_TANH = 0, 1, 2, 3, 4, 5
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
@@ -76,6 +76,8 @@ SIGNATURES = {
     "st2_linear_tc_weight_layout": [_vp, _vp, _i, _i, _vp],
     "st2_linear_tc": [_vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp],
     "st2_attention": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "st2_attention_ex": [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],
+    "st2_embedding_sum_rows": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "st2_lstm_bidir": [_vp, _vp, _vp, _ll, _ll, _ll, _vp, _i, _i, _i, _vp, _vp],
     "st2_kdiff_step": [_vp, _vp, _vp, _f, _f, _f, _f, _vp, _f, _vp, _f, _vp, _i, _vp],
     "st2_scale": [_vp, _f, _vp, _i, _vp],
