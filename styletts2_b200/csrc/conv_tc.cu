@@ -34,29 +34,32 @@ namespace tc {
 
 constexpr int TN = 256;
 constexpr int TM = 128;
-constexpr int CB = 32;
-constexpr int W_STAGES = 4;
-constexpr int W_STAGE_BYTES = 2 * 4 * TM * 16;  // (hi|lo) x 4 k-chunks x 128 co x 16 B
+constexpr int CB = 16;                          // input channels per pipeline block (2 K-chunks of 8 = one UMMA K step)
+constexpr int KCB = CB / 8;                     // K-chunks per block
+constexpr int W_STAGES = 6;
+constexpr int W_STAGE_BYTES = 2 * KCB * TM * 16;  // (hi|lo) x 2 k-chunks x 128 co x 16 B = 8 KB
 constexpr int RW_MAX = 312;                     // TN + (K-1)*dil rounded up to 8, max
 constexpr int RWP_MAX = RW_MAX + 2;             // chunk pitch in rows: == 2 (mod 8) -> conflict-free 128-bit staging stores
-constexpr int ACT_HALF_BYTES = 4 * RWP_MAX * 16; // one of hi / lo for one 32-channel block
+constexpr int ACT_HALF_BYTES = KCB * RWP_MAX * 16;  // one of hi / lo for one 16-channel block
 constexpr int ACT_BUF_BYTES = 2 * ACT_HALF_BYTES;
+constexpr int RAW_STAGES = 4;                   // cp.async ring of raw fp32 frame windows: 3 blocks (60 KB) in flight per SM
+constexpr int RAW_BYTES = CB * RWP_MAX * 4;     // 20 KB
 constexpr int CIN_PAD_MAX = 1120;
 constexpr int NUM_STAGERS = 320;                // 10 warps
 constexpr int NUM_EPI = 256;                    // 8 warps: two per TMEM lane quarter (each takes half of the columns)
 constexpr int THREADS = 64 + NUM_STAGERS + NUM_EPI;  // 640 = 20 warps (register allocation granularity: 4 warps)
-constexpr int STG_RG = NUM_STAGERS / 4;         // 80 frame-row groups
 constexpr int TPITCH = 36;                      // epilogue transpose row pitch (floats), 16-byte aligned rows
 
 constexpr int SM_W = 0;
 constexpr int SM_ACT = SM_W + W_STAGES * W_STAGE_BYTES;
-constexpr int SM_COEF = SM_ACT + 2 * ACT_BUF_BYTES;
+constexpr int SM_RAW = SM_ACT + 2 * ACT_BUF_BYTES;
+constexpr int SM_COEF = SM_RAW + RAW_STAGES * RAW_BYTES;
 constexpr int SM_EPI = SM_COEF + 4 * CIN_PAD_MAX * 4;
 constexpr int SM_BAR = SM_EPI + 8 * (32 * TPITCH + 32) * 4;
 constexpr int SM_TOTAL = SM_BAR + 256;
 
 // barrier slots (8 B each) inside SM_BAR
-constexpr int B_WFULL = 0, B_WEMPTY = 4, B_AFULL = 8, B_AEMPTY = 10, B_TFULL = 12, B_TEMPTY = 14, B_COUNT = 16;
+constexpr int B_WFULL = 0, B_WEMPTY = 6, B_AFULL = 12, B_AEMPTY = 14, B_TFULL = 16, B_TEMPTY = 18, B_COUNT = 20;
 
 // Optional per-role cycle trace of CTA 0 (debug/profiling aid; null in production).
 __device__ long long* g_trace = nullptr;
@@ -154,6 +157,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Output channels of a 128-row tile are spread over the four TMEM lane quarters (an epilogue warp can only read the
+// quarter warp_id % 4): quarter q holds channels co0 + q*rq .. + rq-1 with rq = ceil(min(Cout - co0, 128) / 4).  For full
+// tiles rq = 32 (identity); for narrow layers (HiFi-GAN C = 64 / 32, conv_post) all eight epilogue warps get work.
+__host__ __device__ __forceinline__ int rows_per_quarter(int Cout, int cob) {
+  int rem = Cout - cob * TM;
+  if (rem > TM) rem = TM;
+  return (rem + 3) >> 2;
 }
 
 struct TileCoord {
@@ -290,12 +302,9 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
             const uint32_t w_hi = sbase + SM_W + ws * W_STAGE_BYTES;
             const uint32_t w_lo = w_hi + W_STAGE_BYTES / 2;
             const uint32_t row_off = (uint32_t)(tap * a.dil) * 16;
-#pragma unroll
-            for (int k16 = 0; k16 < 2; ++k16) {
-              const uint32_t aoff = (uint32_t)(2 * k16) * lbo_a;
-              const uint32_t boff = (uint32_t)(2 * k16) * lbo_b + row_off;
-              const uint64_t da_hi = make_desc(w_hi + aoff, lbo_a, 128), da_lo = make_desc(w_lo + aoff, lbo_a, 128);
-              const uint64_t db_hi = make_desc(act_hi + boff, lbo_b, 128), db_lo = make_desc(act_lo + boff, lbo_b, 128);
+            {
+              const uint64_t da_hi = make_desc(w_hi, lbo_a, 128), da_lo = make_desc(w_lo, lbo_a, 128);
+              const uint64_t db_hi = make_desc(act_hi + row_off, lbo_b, 128), db_lo = make_desc(act_lo + row_off, lbo_b, 128);
               tc_mma(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
               first = 0;
               tc_mma(d_tmem, da_hi, db_lo, idesc, 1u);
@@ -331,82 +340,107 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     }
   } else if (warp < 2 + NUM_STAGERS / 32) {
     // ================================================================ activation stagers
-    // thread -> one 8-channel K-chunk (kc) and every 64th frame row: the AdaIN / Snake coefficients of its 8
-    // channels live in registers, all loads of a block are issued before any is consumed.
+    // Raw fp32 frame windows travel HBM -> shared memory with cp.async (no registers held while in flight): a ring
+    // of RAW_STAGES 16-channel blocks keeps ~60 KB per SM outstanding, which is what it takes to cover HBM latency.
+    // Conversion (AdaIN affine + Snake/LeakyReLU + bf16 hi/lo split) reads the landed block from shared memory.
     const int st = tid - 64;  // 0..319
-    const int kc = st & 3, rg = st >> 2;  // lanes: 4 K-chunks x 8 consecutive frames (32-byte segments)
-    const int Lin_ = a.Lin, pre_act_ = a.pre_act;
+    const int Lin_ = a.Lin, pre_act_ = a.pre_act, Cin_ = a.Cin;
     const float slope_ = a.pre_slope;
     float* coef = reinterpret_cast<float*>(smem + SM_COEF);
     const int cin_pad = ncb * CB;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total_blocks = my_tiles * ncb;
+    // issue mapping: thread -> one channel of the block (st / 20) and every 20th frame row: pointer increments only
+    const int ich = st / 20, ir0 = st - ich * 20;
+    int i_tile = -1, i_b = 0, i_g0 = 0;  // producer-side tile state (runs 3 blocks ahead of the conversion)
+    const float* i_xb = a.x;
+    auto issue = [&](int g) {
+      if (g < total_blocks) {
+        const int tl = g / ncb, cb = g - tl * ncb;
+        if (tl != i_tile) {
+          i_tile = tl;
+          const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
+          i_b = tc_.b;
+          i_xb = a.x + (long long)tc_.b * a.x_bstride;
+          i_g0 = tc_.tq * TN - a.pad;
+        }
+        const int c = cb * CB + ich;
+        const int rlo = (c < Cin_) ? max(0, -i_g0) : RW;   // rows [rlo, rhi) are inside the tensor; the rest zero-fill
+        const int rhi = min(RW, Lin_ - i_g0);
+        const float* src = i_xb + (long long)min(c, Cin_ - 1) * Lin_ + (i_g0 + ir0);
+        uint32_t dst = sbase + SM_RAW + (g % RAW_STAGES) * RAW_BYTES + (uint32_t)(ich * RWP + ir0) * 4;
+        for (int r = ir0; r < RW; r += 20) {
+          const bool ok = (r >= rlo) && (r < rhi);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(ok ? src : a.x), "r"(ok ? 4 : 0) : "memory");
+          src += 20;
+          dst += 80;
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue(0);
+    issue(1);
+    issue(2);
     int as = 0, aph = 0;
-    int last_b = -1;
-    int sit = 0;
-    constexpr int NR = (RW_MAX + STG_RG - 1) / STG_RG;  // 6 row iterations max
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++sit) {
-      const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
-      const long long stt0 = clock64();
-      long long w_ae = 0;
-      if (tc_.b != last_b) {
-        asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));  // everybody done reading the old table
+    int last_b = -1, c_tile = -1, c_b = 0, c_g0 = 0;
+    const int kc = st & 1, rg = st >> 1;  // conversion mapping: 2 K-chunks x 160 row groups
+    constexpr int NRC = (RW_MAX + 159) / 160;
+    for (int g = 0; g < total_blocks; ++g) {
+      const int tl = g / ncb, cb = g - tl * ncb;
+      if (tl != c_tile) {
+        c_tile = tl;
+        const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
+        c_b = tc_.b;
+        c_g0 = tc_.tq * TN - a.pad;
+      }
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));  // block g landed for everybody; block g-1 fully converted
+      issue(g + 3);                                          // reuses the slot of block g-1
+      if (c_b != last_b) {
         for (int c = st; c < cin_pad; c += NUM_STAGERS) {
           float pa = 0.f, pb = 0.f, al = 1.f;  // padded channels stage exact zeros
-          if (c < a.Cin) {
+          if (c < Cin_) {
             pa = 1.f;
-            if (a.pre_a) { pa = a.pre_a[tc_.b * a.Cin + c]; pb = a.pre_b[tc_.b * a.Cin + c]; }
-            if (a.pre_act == ST2_ACT_SNAKE) al = a.pre_alpha[c];
+            if (a.pre_a) { pa = a.pre_a[c_b * Cin_ + c]; pb = a.pre_b[c_b * Cin_ + c]; }
+            if (pre_act_ == ST2_ACT_SNAKE) al = a.pre_alpha[c];
           }
           coef[c] = pa; coef[CIN_PAD_MAX + c] = pb; coef[2 * CIN_PAD_MAX + c] = al; coef[3 * CIN_PAD_MAX + c] = 1.0f / al;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));
-        last_b = tc_.b;
+        asm volatile("bar.sync 2, %0;" ::"n"(NUM_STAGERS));
+        last_b = c_b;
       }
-      const float* xb = a.x + (long long)tc_.b * a.x_bstride;
-      const int g0 = tc_.tq * TN - a.pad;  // global time of window row 0
-      for (int cb = 0; cb < ncb; ++cb) {
-        const int c0 = cb * CB + kc * 8;
-        float pa[8], pb[8], al[8], ia[8];
+      const int c0 = cb * CB + kc * 8;
+      float pa[8], pb[8], al[8], ia[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          pa[j] = coef[c0 + j]; pb[j] = coef[CIN_PAD_MAX + c0 + j]; al[j] = coef[2 * CIN_PAD_MAX + c0 + j];
-          ia[j] = coef[3 * CIN_PAD_MAX + c0 + j];
-        }
-        // 8 channel rows of this K-chunk: base pointer + j*Lin (channels beyond Cin are clamped; their pa=pb=0)
-        const int cclamp = min(c0, max(a.Cin - 8, 0));
-        const float* xc0 = xb + (long long)cclamp * Lin_;
-        const int jmax = a.Cin - 1 - cclamp;  // last valid j offset (>= 0)
-        uint8_t* hi = smem + SM_ACT + as * ACT_BUF_BYTES;
-        uint8_t* lo = hi + ACT_HALF_BYTES;
-        // all loads of this thread (up to 6 frame rows x 8 channels) are in flight before the buffer wait / first use
-        float xv[NR][8];
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-          const int r = rg + STG_RG * i;
-          const int g = g0 + r;
-          const bool ok = (r < RW) && (g >= 0) && (g < Lin_);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xv[i][j] = ok ? __ldg(xc0 + (long long)min(j + (c0 - cclamp), jmax) * Lin_ + g) : 0.f;
-        }
-        w_ae += mbar_wait_timed(BAR(B_AEMPTY + as), aph ^ 1);
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-          const int r = rg + STG_RG * i;
-          if (r < RW) {
-            const int g = g0 + r;
-            const bool inb = (g >= 0) && (g < Lin_);
-            uint8_t* hd = hi + (size_t)(kc * RWP + r) * 16;
-            uint8_t* ld = lo + (size_t)(kc * RWP + r) * 16;
-            if (pre_act_ == ST2_ACT_SNAKE) stage_row<ST2_ACT_SNAKE>(xv[i], pa, pb, al, ia, slope_, inb, hd, ld);
-            else if (pre_act_ == ST2_ACT_LRELU) stage_row<ST2_ACT_LRELU>(xv[i], pa, pb, al, ia, slope_, inb, hd, ld);
-            else stage_row<ST2_ACT_NONE>(xv[i], pa, pb, al, ia, slope_, inb, hd, ld);
-          }
-        }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        mbar_arrive(BAR(B_AFULL + as));
-        if (++as == 2) { as = 0; aph ^= 1; }
+      for (int j = 0; j < 8; ++j) {
+        pa[j] = coef[c0 + j]; pb[j] = coef[CIN_PAD_MAX + c0 + j]; al[j] = coef[2 * CIN_PAD_MAX + c0 + j];
+        ia[j] = coef[3 * CIN_PAD_MAX + c0 + j];
       }
-      if (st == 0) { trace_put(2, sit, 0, stt0); trace_put(2, sit, 1, clock64()); trace_put(2, sit, 2, w_ae); }
+      const float* raw = reinterpret_cast<const float*>(smem + SM_RAW + (g % RAW_STAGES) * RAW_BYTES) + (kc * 8) * RWP;
+      mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
+      uint8_t* hi = smem + SM_ACT + as * ACT_BUF_BYTES;
+      uint8_t* lo = hi + ACT_HALF_BYTES;
+#pragma unroll
+      for (int i = 0; i < NRC; ++i) {
+        const int r = rg + 160 * i;
+        if (r < RW) {
+          const int gt = c_g0 + r;
+          const bool inb = (gt >= 0) && (gt < Lin_);
+          float xv[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[j] = raw[j * RWP + r];
+          uint8_t* hd = hi + (size_t)(kc * RWP + r) * 16;
+          uint8_t* ld = lo + (size_t)(kc * RWP + r) * 16;
+          if (pre_act_ == ST2_ACT_SNAKE) stage_row<ST2_ACT_SNAKE>(xv, pa, pb, al, ia, slope_, inb, hd, ld);
+          else if (pre_act_ == ST2_ACT_LRELU) stage_row<ST2_ACT_LRELU>(xv, pa, pb, al, ia, slope_, inb, hd, ld);
+          else stage_row<ST2_ACT_NONE>(xv, pa, pb, al, ia, slope_, inb, hd, ld);
+        }
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(BAR(B_AFULL + as));
+      if (++as == 2) { as = 0; aph ^= 1; }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else {
     // ================================================================ epilogue (8 warps)
     const int ewi = warp - (2 + NUM_STAGERS / 32);  // 0..7
@@ -422,10 +456,11 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
       const int buf = it & 1;
-      const int co_base = tc_.cob * TM + ew * 32;
+      const int rq = rows_per_quarter(Cout_, tc_.cob);
+      const int co_base = tc_.cob * TM + ew * rq;
       const int t0 = tc_.tq * TN;
       const int ncols = min(TN, Lq_ - t0);
-      const int rmax = min(32, Cout_ - co_base);  // warp-uniform (may be <= 0 for padded channel blocks)
+      const int rmax = min(rq, Cout_ - co_base);  // warp-uniform (may be <= 0 for padded channel blocks)
       bsm[lane] = (a.bias && lane < rmax) ? a.bias[co_base + lane] : 0.f;
       const long long ett0 = clock64();
       const long long w_tf = mbar_wait_timed(BAR(B_TFULL + buf), (it >> 1) & 1);
@@ -561,19 +596,21 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
 // fp32 [Cout,Cin,K] -> bf16 hi/lo stage blocks [K][n_cob][ncb][2][4][128][8]
 __global__ void conv_tc_weight_layout_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int K,
                                              int n_cob, int ncb) {
-  const long long total = (long long)K * n_cob * ncb * 2 * 4 * TM * 8;
+  const long long total = (long long)K * n_cob * ncb * 2 * KCB * TM * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
     const int j = (int)(r % 8); r /= 8;
     const int col = (int)(r % TM); r /= TM;
-    const int kc = (int)(r % 4); r /= 4;
+    const int kc = (int)(r % KCB); r /= KCB;
     const int hl = (int)(r % 2); r /= 2;
     const int cb = (int)(r % ncb); r /= ncb;
     const int cob = (int)(r % n_cob); r /= n_cob;
     const int tap = (int)r;
-    const int co = cob * TM + col, ci = cb * CB + kc * 8 + j;
+    const int rq = rows_per_quarter(Cout, cob);
+    const int qq = col >> 5, rr = col & 31;
+    const int co = cob * TM + qq * rq + rr, ci = cb * CB + kc * 8 + j;
     float v = 0.f;
-    if (co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * K + tap];
+    if (rr < rq && co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * K + tap];
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     out[i] = hl == 0 ? h : __float2bfloat16_rn(v - __bfloat162float(h));
   }
@@ -582,22 +619,24 @@ __global__ void conv_tc_weight_layout_kernel(const float* __restrict__ w, __nv_b
 // ConvTranspose1d weight [Cin,Cout,K] -> S per-phase tensor-core blocks (phase r = J-tap stride-1 conv, see conv.cu)
 __global__ void convT_tc_weight_layout_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Cout, int K,
                                               int S, int P, int J, int n_cob, int ncb) {
-  const long long per_phase = (long long)J * n_cob * ncb * 2 * 4 * TM * 8;
+  const long long per_phase = (long long)J * n_cob * ncb * 2 * KCB * TM * 8;
   const long long total = per_phase * S;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ph = (int)(i / per_phase);
     long long r = i % per_phase;
     const int j = (int)(r % 8); r /= 8;
     const int col = (int)(r % TM); r /= TM;
-    const int kc = (int)(r % 4); r /= 4;
+    const int kc = (int)(r % KCB); r /= KCB;
     const int hl = (int)(r % 2); r /= 2;
     const int cb = (int)(r % ncb); r /= ncb;
     const int cob = (int)(r % n_cob); r /= n_cob;
     const int kp = (int)r;  // tap of the phase conv
-    const int co = cob * TM + col, ci = cb * CB + kc * 8 + j;
+    const int rq = rows_per_quarter(Cout, cob);
+    const int qq = col >> 5, rr = col & 31;
+    const int co = cob * TM + qq * rq + rr, ci = cb * CB + kc * 8 + j;
     const int kk = (J - 1 - kp) * S + ((ph + P) % S);
     float v = 0.f;
-    if (co < Cout && ci < Cin && kk < K) v = w[((long long)ci * Cout + co) * K + kk];
+    if (rr < rq && co < Cout && ci < Cin && kk < K) v = w[((long long)ci * Cout + co) * K + kk];
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     out[i] = hl == 0 ? h : __float2bfloat16_rn(v - __bfloat162float(h));
   }
