@@ -191,7 +191,7 @@ int st2_embedding_sum_rows(const long long* tokens, const float* word, const flo
  * gx [B*L, 8H] = x W_ih^T + b_ih + b_hh for (fwd | bwd); whh [2][4H][H]; out element
  * (b,t,dir*H+j) at out + b*o_bs + t*o_ts + (dir*H+j)*o_cs.  lengths (int32 [B]) or NULL gives
  * pack_padded_sequence semantics (backward pass starts at lengths[b]-1; padded steps = 0).
- * work: >= 6*B*H floats of scratch. */
+ * work: >= 6*B*H + 64 floats of scratch. */
 int st2_lstm_bidir(const float* gx, const float* whh, float* out, long long o_bs, long long o_ts, long long o_cs,
                    const int* lengths, int B, int L, int H, float* work, void* stream);
 
@@ -227,10 +227,19 @@ int st2_expand_cl(const float* src, const int* tok, int B, int C, int N, int T, 
  * SineGen + SourceModuleHnNSF (istftnet.py:146-247,283-297 == hifigan.py:117-218,254-268):
  * f0 [B,F] (F = 2T frames), nearest-upsampled by `scale`; 9 harmonics; fp64 phase accumulation as
  * torch.cumsum on CPU; linear interpolation with PyTorch's align_corners=False rule;
- * uv = f0 > 10; noise [B, F*scale, 9] = the randn_like draw (istftnet.py:242), injected;
+ * uv = f0 > 10; noise [B, F*scale, 9] = the randn_like draw (istftnet.py:242) injected (parity mode), or NULL:
+ * the kernel draws it in place with Philox4x32-10 + Box-Muller from (seed, offset) (throughput mode);
  * lin_w [9], lin_b [1] = m_source.l_linear; out [B, F*scale] = tanh(linear(.)). */
 int st2_sine_source(const float* f0, int B, int F, int scale, const float* noise, const float* lin_w,
-                    const float* lin_b, float* out, float* phase_work /* B*9*F floats */, void* stream);
+                    const float* lin_b, float* out, float* phase_work /* B*9*F floats */, unsigned long long seed,
+                    unsigned long long offset, const unsigned long long* epoch /* device, nullable */, void* stream);
+/* out[0..n) ~ N(0,1): Philox4x32-10 counter RNG + Box-Muller, stream (seed, offset) -- stands in for torch.randn_like on
+ * the path (sampler.py:509) in throughput mode. */
+int st2_randn(float* out, long long n, unsigned long long seed, unsigned long long offset,
+              const unsigned long long* epoch /* device, nullable */, void* stream);
+/* *epoch += 1 on the stream: the draw counter's upper words live in device memory so that a captured CUDA graph
+ * produces fresh noise at every replay. */
+int st2_rng_advance(unsigned long long* epoch, void* stream);
 /* TorchSTFT.transform (istftnet.py:91-97): n_fft 20, hop 5, hann, center/reflect.
  * x [B,L] -> har [B,22,L/5+1] = [|X| ; angle X]. */
 int st2_stft20(const float* x, int B, int L, float* har, void* stream);

@@ -102,9 +102,7 @@ __global__ void __launch_bounds__(LSTM_UT* LSTM_BT) lstm_step_kernel(
 __global__ void __launch_bounds__(LSTM_UT* LSTM_BT) lstm_persistent_kernel(
     const float* __restrict__ gx, const float* __restrict__ whh, float* __restrict__ out, long long o_bs, long long o_ts,
     long long o_cs, const int* __restrict__ lengths, int B, int L, int H, float* __restrict__ h0, float* __restrict__ h1,
-    float* __restrict__ c_state) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+    float* __restrict__ c_state, unsigned int* __restrict__ step_bar) {
   extern __shared__ __align__(16) float sm[];
   const int HP = H + 4;
   float* ws = sm;
@@ -133,11 +131,29 @@ __global__ void __launch_bounds__(LSTM_UT* LSTM_BT) lstm_persistent_kernel(
   const float* w2 = ws + (2 * LSTM_UT + u) * HP;
   const float* w3 = ws + (3 * LSTM_UT + u) * HP;
   const int nbt = (B + LSTM_BT - 1) / LSTM_BT;
+  const unsigned int nct = gridDim.x;                 // CTAs of this direction
+  unsigned int* bar = step_bar + dir * 32;            // one 128-byte line per direction
+  float creg = 0.f;                                   // cell state lives in a register when one batch tile covers B
   for (int step = 0; step < L; ++step) {
     const float* hprev = ((step & 1) ? h1 : h0) + (long long)dir * B * H;
     float* hnext = ((step & 1) ? h0 : h1) + (long long)dir * B * H;
     for (int bt = 0; bt < nbt; ++bt) {
       const int b0 = bt * LSTM_BT;
+      const int b = b0 + bl;
+      const bool live = b < B && j < H;
+      // everything that does not depend on h_{t-1} is fetched first, under the latency of the h staging
+      int len = L, t = 0;
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, cprev = creg;
+      float* cp = c_state + (long long)dir * B * H + (long long)b * H + j;
+      if (live) {
+        len = lengths ? lengths[b] : L;
+        if (step < len) {
+          t = dir == 0 ? step : (len - 1 - step);
+          const float* g = gx + ((long long)b * L + t) * (8 * H) + (long long)dir * 4 * H + j;
+          g0 = __ldg(g); g1 = __ldg(g + H); g2 = __ldg(g + 2 * H); g3 = __ldg(g + 3 * H);
+          if (nbt > 1) cprev = *cp;
+        }
+      }
       __syncthreads();  // previous users of hs are done (also orders the one-time ws staging)
       {
         const int n4 = LSTM_BT * H4;
@@ -151,14 +167,11 @@ __global__ void __launch_bounds__(LSTM_UT* LSTM_BT) lstm_persistent_kernel(
         }
       }
       __syncthreads();
-      const int b = b0 + bl;
-      if (b < B && j < H) {
-        const int len = lengths ? lengths[b] : L;
+      if (live) {
         float* hn = hnext + (long long)b * H + j;
         if (step >= len) {
           *hn = hs[bl * HP + j];
         } else {
-          const int t = dir == 0 ? step : (len - 1 - step);
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
           const float* hr = hs + bl * HP;
 #pragma unroll 4
@@ -173,21 +186,32 @@ __global__ void __launch_bounds__(LSTM_UT* LSTM_BT) lstm_persistent_kernel(
             a2 = fmaf(hv.x, x2.x, a2); a2 = fmaf(hv.y, x2.y, a2); a2 = fmaf(hv.z, x2.z, a2); a2 = fmaf(hv.w, x2.w, a2);
             a3 = fmaf(hv.x, x3.x, a3); a3 = fmaf(hv.y, x3.y, a3); a3 = fmaf(hv.z, x3.z, a3); a3 = fmaf(hv.w, x3.w, a3);
           }
-          const float* g = gx + ((long long)b * L + t) * (8 * H) + (long long)dir * 4 * H + j;
-          const float gi = sigmoidf_(g[0] + a0);
-          const float gf = sigmoidf_(g[H] + a1);
-          const float gg = tanhf(g[2 * H] + a2);
-          const float go = sigmoidf_(g[3 * H] + a3);
-          float* cp = c_state + (long long)dir * B * H + (long long)b * H + j;
-          const float c = gf * (*cp) + gi * gg;
-          *cp = c;
+          const float gi = sigmoidf_(g0 + a0);
+          const float gf = sigmoidf_(g1 + a1);
+          const float gg = tanhf(g2 + a2);
+          const float go = sigmoidf_(g3 + a3);
+          const float c = gf * cprev + gi * gg;
+          if (nbt > 1) *cp = c; else creg = c;
           const float h = go * tanhf(c);
           *hn = h;
           out[(long long)b * o_bs + (long long)t * o_ts + (long long)(dir * H + j) * o_cs] = h;
         }
       }
     }
-    grid.sync();
+    // per-direction step barrier (the two directions never exchange data): release our h writes, then wait
+    // until all `nct` CTAs of this direction have arrived `step+1` times.  Co-residency of the CTAs is
+    // guaranteed by the cooperative launch.
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      atomicAdd(bar, 1u);
+      const unsigned int want = nct * (unsigned int)(step + 1);
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+      } while (seen < want);
+    }
+    __syncthreads();
   }
 }
 
@@ -203,7 +227,8 @@ extern "C" int st2_lstm_bidir(const float* gx, const float* whh, float* out, lon
   float* h0 = work;
   float* h1 = work + n;
   float* c = work + 2 * n;
-  cudaError_t e = cudaMemsetAsync(work, 0, 3 * n * sizeof(float), st);
+  unsigned int* step_bar = reinterpret_cast<unsigned int*>(work + 3 * n);   // 64 words: per-direction step barriers
+  cudaError_t e = cudaMemsetAsync(work, 0, (3 * n + 64) * sizeof(float), st);
   if (e != cudaSuccess) { set_error("st2_lstm_bidir", e); return (int)e; }
   const size_t smem = (size_t)(4 * LSTM_UT + LSTM_BT) * (H + 4) * sizeof(float);
   static bool attr_done = false;
@@ -224,7 +249,8 @@ extern "C" int st2_lstm_bidir(const float* gx, const float* whh, float* out, lon
   if (coop && cdiv(H, LSTM_UT) * 2 <= num_sms) {
     dim3 pgrid(cdiv(H, LSTM_UT), 2);
     void* args[] = {(void*)&gx, (void*)&whh, (void*)&out, (void*)&o_bs, (void*)&o_ts, (void*)&o_cs, (void*)&lengths,
-                    (void*)&B,  (void*)&L,   (void*)&H,   (void*)&h0,   (void*)&h1,   (void*)&c};
+                    (void*)&B,  (void*)&L,   (void*)&H,   (void*)&h0,   (void*)&h1,   (void*)&c,
+                    (void*)&step_bar};
     e = cudaLaunchCooperativeKernel((const void*)lstm_persistent_kernel, pgrid, dim3(LSTM_UT * LSTM_BT), args, smem, st);
     if (e != cudaSuccess) { set_error("st2_lstm_bidir (cooperative launch)", e); return (int)e; }
     ++g_launches;

@@ -14,6 +14,55 @@ extern long long g_launches;
 
 constexpr int NH = 9;  // fundamental + 8 overtones (istftnet.py:313)
 
+// Philox4x32-10 counter-based generator (Salmon et al. 2011) + Box-Muller: the throughput mode draws the
+// randn_like noise of the reference (istftnet.py:242, sampler.py:509) on the device without a library call.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = ((float)a + 0.5f) * 2.3283064365386963e-10f;  // (0,1)
+  const float u2 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincosf(6.28318530717958647692f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+// 4 standard normals for counter index i of stream (seed, offset)
+// `epoch` (read from device memory, so a captured CUDA graph draws fresh noise on every replay) fills the upper counter words.
+__device__ __forceinline__ float4 randn4(unsigned long long seed, unsigned long long offset, unsigned long long epoch,
+                                         unsigned long long i) {
+  const unsigned long long c = offset + i;
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)epoch, (uint32_t)(epoch >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float2 a = box_muller(r.x, r.y), b = box_muller(r.z, r.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__global__ void rng_advance_kernel(unsigned long long* epoch) { *epoch += 1ull; }
+
+__global__ void randn_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
+                             const unsigned long long* __restrict__ epoch_p) {
+  const unsigned long long epoch = epoch_p ? *epoch_p : 0ull;
+  const long long n4 = (n + 3) >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = randn4(seed, offset, epoch, (unsigned long long)i);
+    const long long j = i * 4;
+    if (j < n) out[j] = v.x;
+    if (j + 1 < n) out[j + 1] = v.y;
+    if (j + 2 < n) out[j + 2] = v.z;
+    if (j + 3 < n) out[j + 3] = v.w;
+  }
+}
+
 __device__ __forceinline__ float torch_remainder1(float x) {
   // torch `% 1` for floats: fmod, then shift into [0,1) when negative (istftnet.py:152)
   float r = fmodf(x, 1.0f);
@@ -44,7 +93,8 @@ __global__ void sine_phase_kernel(const float* __restrict__ f0, int B, int F, fl
 
 __global__ void sine_source_kernel(const float* __restrict__ f0, const float* __restrict__ phase, int F, int scale,
                                    const float* __restrict__ noise, const float* __restrict__ lin_w,
-                                   const float* __restrict__ lin_b, float* __restrict__ out) {
+                                   const float* __restrict__ lin_b, float* __restrict__ out, unsigned long long seed,
+                                   unsigned long long offset, const unsigned long long* __restrict__ epoch_p) {
   const int b = blockIdx.y;
   const long long L = (long long)F * scale;
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -62,14 +112,27 @@ __global__ void sine_source_kernel(const float* __restrict__ f0, const float* __
   const float f0v = f0[(long long)b * F + (int)(t / scale)];  // nearest upsample (istftnet.py:352)
   const float uv = f0v > 10.0f ? 1.0f : 0.0f;
   const float noise_amp = uv > 0.f ? 0.003f : __fdiv_rn(0.1f, 3.0f);
-  const float* nz = noise + ((long long)b * L + t) * NH;
+  float nzv[12];
+  if (noise) {
+    const float* nz = noise + ((long long)b * L + t) * NH;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) nzv[h] = nz[h];
+  } else {  // throughput mode: draw the 9 normals of this sample in place (3 Philox calls)
+    const unsigned long long e = ((unsigned long long)b * (unsigned long long)L + (unsigned long long)t) * 3ull;
+    const unsigned long long epoch = epoch_p ? *epoch_p : 0ull;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float4 v = randn4(seed, offset, epoch, e + q);
+      nzv[4 * q] = v.x; nzv[4 * q + 1] = v.y; nzv[4 * q + 2] = v.z; nzv[4 * q + 3] = v.w;
+    }
+  }
   float accv = lin_b[0];
 #pragma unroll
   for (int h = 0; h < NH; ++h) {
     const float* pr = phase + ((long long)b * NH + h) * F;
     const float ph = fmaf(l0, pr[i0], __fmul_rn(l1, pr[i1]));
     const float sw = __fmul_rn(sinf(ph), 0.1f);
-    const float v = __fadd_rn(__fmul_rn(sw, uv), __fmul_rn(noise_amp, nz[h]));
+    const float v = __fadd_rn(__fmul_rn(sw, uv), __fmul_rn(noise_amp, nzv[h]));
     accv = fmaf(lin_w[h], v, accv);
   }
   out[(long long)b * L + t] = tanhf(accv);
@@ -193,14 +256,34 @@ using namespace st2;
 
 extern "C" {
 
+int st2_rng_advance(unsigned long long* epoch, void* stream) {
+  ST2_REQUIRE(epoch, "st2_rng_advance", "bad args");
+  rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(epoch);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_rng_advance");
+  return 0;
+}
+
+int st2_randn(float* out, long long n, unsigned long long seed, unsigned long long offset, const unsigned long long* epoch,
+              void* stream) {
+  ST2_REQUIRE(out && n > 0, "st2_randn", "bad args");
+  const long long n4 = (n + 3) / 4;
+  const int grid = (int)((n4 + 255) / 256 > 4096 ? 4096 : (n4 + 255) / 256);
+  randn_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, epoch);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_randn");
+  return 0;
+}
+
 int st2_sine_source(const float* f0, int B, int F, int scale, const float* noise, const float* lin_w, const float* lin_b,
-                    float* out, float* phase_work, void* stream) {
-  ST2_REQUIRE(f0 && noise && lin_w && lin_b && out && phase_work && B > 0 && F > 0 && scale > 0, "st2_sine_source", "bad args");
+                    float* out, float* phase_work, unsigned long long seed, unsigned long long offset,
+                    const unsigned long long* epoch, void* stream) {
+  ST2_REQUIRE(f0 && lin_w && lin_b && out && phase_work && B > 0 && F > 0 && scale > 0, "st2_sine_source", "bad args");
   cudaStream_t st = (cudaStream_t)stream;
   sine_phase_kernel<<<cdiv(B * NH, 64), 64, 0, st>>>(f0, B, F, (float)scale, phase_work);
   ++g_launches;
   const long long L = (long long)F * scale;
-  sine_source_kernel<<<dim3(cdiv(L, 256), B), 256, 0, st>>>(f0, phase_work, F, scale, noise, lin_w, lin_b, out);
+  sine_source_kernel<<<dim3(cdiv(L, 256), B), 256, 0, st>>>(f0, phase_work, F, scale, noise, lin_w, lin_b, out, seed, offset, epoch);
   ++g_launches;
   ST2_CHECK_LAUNCH("st2_sine_source");
   return 0;

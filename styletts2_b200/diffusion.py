@@ -253,7 +253,7 @@ class ADPM2Sampler(Sampler):
             sigma_up, sigma_down, sigma_mid = self.get_sigmas(sigma, sigma_next)
             dt_mid = float(sigma_mid - sigma)          # fp32 tensor arithmetic, as the reference
             dt_down = float(sigma_down - sigma)        # python float - fp32 tensor -> fp32 tensor
-            eps = step_noises[i] if step_noises is not None else torch.randn_like(x)
+            eps = step_noises[i] if step_noises is not None else ops.randn_like(x)
             x_mid = fn.step(x, float(sigma), x, dt_mid)
             x = fn.step(x_mid, float(sigma_mid), x, dt_down, eps=eps, sigma_up=float(torch.tensor(sigma_up, dtype=torch.float32)))
         return x

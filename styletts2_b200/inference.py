@@ -38,6 +38,7 @@ class Synthesizer:
         self.multispeaker = bool(model_cfg["multispeaker"])
         self.hifigan = model_cfg["decoder"]["type"] == "hifigan"
         self.sampler = make_sampler(model)
+        ops._rng_epoch(self.device)   # allocate the device-resident draw epoch outside any graph capture
 
     @torch.no_grad()
     def synthesize(self, tokens, input_lengths, bert_dur, noise, *, diffusion_steps=5, embedding_scale=1.0, ref_s=None,
@@ -60,6 +61,8 @@ class Synthesizer:
                 ev.record()
                 stage_marks.append((name, ev))
         mark("start")
+        if "step_noises" not in rng or "sine_noise" not in rng:
+            ops.rng_advance(dev)   # throughput mode: new Philox epoch per call (also per CUDA-graph replay)
         mask = length_to_mask(input_lengths, N)
         if bert_dur is None:   # PL-BERT on our kernels (styletts2_b200.plbert.PLBert passed to build_model)
             bert_dur = m.bert(tokens, attention_mask=(~mask).int())
@@ -164,7 +167,7 @@ class Synthesizer:
         tk = torch.tensor([list(tokens)], dtype=torch.long, device=dev)
         lens = torch.tensor([tk.shape[1]], dtype=torch.long, device=dev)
         if noise is None:
-            noise = torch.randn(1, 1, 256, device=dev)
+            noise = ops.randn_like(torch.empty(1, 1, 256, device=dev))
         out = self.synthesize(tk, lens, bert_dur.to(dev), noise.to(dev), diffusion_steps=diffusion_steps,
                               embedding_scale=embedding_scale, ref_s=None if ref_s is None else ref_s.to(dev),
                               alpha=alpha, beta=beta)

@@ -529,10 +529,6 @@ class SourceModuleHnNSF(nn.Module):
     def forward(self, f0_curve, noise=None):
         """f0_curve [B,2T] (NOT pre-upsampled: the nearest x300 upsample is fused) -> har_source [B, 600T].
         noise: the randn_like draw of istftnet.py:242 ([B,L,9]); generated on device if None."""
-        B, F = f0_curve.shape
-        Ls = F * self.upsample_scale
-        if noise is None:
-            noise = torch.randn(B, Ls, self.harmonic_num + 1, device=f0_curve.device)
         return ops.sine_source(f0_curve, self.upsample_scale, noise, self.l_linear.weight.view(-1), self.l_linear.bias)
 
 

@@ -309,7 +309,7 @@ def attention(q, kv, B, N, H=8, D=64):
 
 
 def lstm_bidir(gx, whh, out, o_bs, o_ts, o_cs, B, Lr, H, lengths=None):
-    work = empty(6 * B * H, device=gx.device)
+    work = empty(6 * B * H + 64, device=gx.device)
     L.call("st2_lstm_bidir", ptr(gx), ptr(whh), ptr(out), o_bs, o_ts, o_cs, ptr(lengths), B, Lr, H, ptr(work), stream_ptr())
     return out
 
@@ -390,14 +390,54 @@ def expand_cl(src, tok, out=None):
 
 
 # ------------------------------------------------------------------ source / stft
+_RNG = {"seed": 0x5EED5EED, "offset": 0, "epoch": {}}
+
+
+def manual_seed(seed: int):
+    """Seed of the library's own Philox stream (throughput mode draws)."""
+    _RNG["seed"], _RNG["offset"] = int(seed) & 0xFFFFFFFFFFFFFFFF, 0
+    for e in _RNG["epoch"].values():
+        e.zero_()
+
+
+def _rng_epoch(device):
+    """device-resident draw epoch (int64[1]); bumped by rng_advance() once per synthesize call."""
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    e = _RNG["epoch"].get(key)
+    if e is None:
+        e = torch.zeros(1, dtype=torch.int64, device=dev)
+        _RNG["epoch"][key] = e
+    return e
+
+
+def rng_advance(device):
+    L.call("st2_rng_advance", ptr(_rng_epoch(device)), stream_ptr())
+
+
+def _rng_take(n_counters: int):
+    off = _RNG["offset"]
+    _RNG["offset"] = off + int(n_counters)
+    return _RNG["seed"], off
+
+
+def randn_like(x):
+    """N(0,1) draw with the library's Philox kernel (stands in for torch.randn_like on the path)."""
+    out = torch.empty_like(x, memory_format=torch.contiguous_format)
+    seed, off = _rng_take((x.numel() + 3) // 4)
+    L.call("st2_randn", ptr(out), x.numel(), seed, off, ptr(_rng_epoch(x.device)), stream_ptr())
+    return out
+
+
 def sine_source(f0, scale_, noise, lin_w, lin_b):
-    """f0 [B,F] -> [B, F*scale]; noise [B,F*scale,9]"""
+    """f0 [B,F] -> [B, F*scale]; noise [B,F*scale,9] (injected) or None (drawn in the kernel)"""
     f0 = f0.contiguous()
     B, F = f0.shape
     out = empty(B, F * scale_, device=f0.device)
     work = empty(B * 9 * F, device=f0.device)
-    L.call("st2_sine_source", ptr(f0), B, F, scale_, ptr(noise.contiguous()), ptr(lin_w.contiguous()), ptr(lin_b), ptr(out),
-           ptr(work), stream_ptr())
+    seed, off = (0, 0) if noise is not None else _rng_take(B * F * scale_ * 3)
+    L.call("st2_sine_source", ptr(f0), B, F, scale_, ptr(noise.contiguous() if noise is not None else None), ptr(lin_w.contiguous()),
+           ptr(lin_b), ptr(out), ptr(work), seed, off, ptr(_rng_epoch(f0.device)) if noise is None else None, stream_ptr())
     return out
 
 

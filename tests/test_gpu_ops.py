@@ -333,3 +333,40 @@ def test_kdiff_step_and_small_ops():
     assert torch.equal(e.cpu(), ref)
     h = rnd(3 * 7, 64, seed=3)
     assert maxdiff(ops.mean_rows(h.to(D), 3, 7), h.view(3, 7, 64).mean(1)) < 1e-6
+
+
+@pytest.mark.gpu
+def test_philox_randn_statistics_and_epoch():
+    """st2_randn: N(0,1) moments, stream reproducibility, and a fresh draw after st2_rng_advance."""
+    from styletts2_b200 import ops
+    ops.manual_seed(1234)
+    x = torch.empty(1 << 22, device="cuda")
+    a = ops.randn_like(x)
+    assert abs(a.mean().item()) < 3e-3 and abs(a.std().item() - 1.0) < 3e-3
+    assert abs((a ** 3).mean().item()) < 1e-2 and abs((a ** 4).mean().item() - 3.0) < 3e-2
+    # lag-1 / lag-4 correlation of a counter-based stream
+    assert abs((a[1:] * a[:-1]).mean().item()) < 3e-3 and abs((a[4:] * a[:-4]).mean().item()) < 3e-3
+    ops.manual_seed(1234)
+    b = ops.randn_like(x)
+    assert torch.equal(a, b)
+    ops.manual_seed(1234)
+    ops.rng_advance(x.device)
+    c = ops.randn_like(x)
+    assert not torch.equal(a, c) and abs((a * c).mean().item()) < 3e-3
+
+
+@pytest.mark.gpu
+def test_sine_source_in_kernel_noise_matches_injected_statistics():
+    """noise=None draws the 9 normals in the kernel: unvoiced frames give tanh(w . (0.1/3 * n) + b)."""
+    from styletts2_b200 import ops
+    ops.manual_seed(7)
+    B, F, scale = 2, 64, 300
+    f0 = torch.zeros(B, F, device="cuda")          # all unvoiced -> pure noise branch
+    w = torch.full((9,), 0.5, device="cuda")
+    bias = torch.zeros(1, device="cuda")
+    y = ops.sine_source(f0, scale, None, w, bias)
+    pre = torch.atanh(y.clamp(-0.999999, 0.999999))
+    want_std = (0.1 / 3.0) * 0.5 * 3.0               # sqrt(9) * 0.5 * 0.1/3
+    assert abs(pre.mean().item()) < 1e-3 and abs(pre.std().item() / want_std - 1.0) < 2e-2
+    y2 = ops.sine_source(f0, scale, None, w, bias)   # offset advanced -> different draw
+    assert not torch.equal(y, y2)
