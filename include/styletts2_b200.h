@@ -247,6 +247,46 @@ int st2_stft20(const float* x, int B, int L, float* har, void* stream);
  * spec=exp(x[:11]), phase=sin(x[11:]) -> istft (n_fft 20, hop 5) -> wav [B, 5*(Fr-1)]. */
 int st2_istft20_expsin(const float* x, int B, int Fr, float* wav, void* stream);
 
+/* ------------------------------------------------------------------ reference-style path
+ * compute_style (Demo/Inference_LibriTTS.ipynb cell 5): wave -> log-mel -> StyleEncoder x2 (models.py:139-164).
+ *
+ * spectral_norm(nn.Conv2d) in eval mode (models.py:36-38,109-114,142,152): sigma = u . (W_mat v) with the stored
+ * power-iteration vectors; wt[(ci*KH*KW + k) * Cout + co] = weight_orig[co][ci][k] / sigma  (n = Cin/groups*KH*KW).
+ * sigma_work: 1 float of device scratch (receives sigma). */
+int st2_spectral_norm_fold(const float* weight_orig, const float* u, const float* v, int Cout, int n, float* wt,
+                           float* sigma_work, void* stream);
+/* Dense stride-1 Conv2d with the ResBlk elementwise ops fused (models.py:116-137):
+ * out = (conv2d(pre(x)) + bias [+ res]) * out_scale, pre = LeakyReLU(slope) when pre_act != 0.
+ * x [B,Cin,H,W]; wt from st2_spectral_norm_fold ([Cin*KH*KW][Cout]); out/res [B,Cout,Ho,Wo] with
+ * Ho = H + 2*pad - KH + 1.  KHxKW in {1x1, 3x3, 5x5}. */
+typedef struct st2_conv2d_args {
+  const float* x;
+  const float* wt;
+  const float* bias;   /* [Cout] or NULL (conv1x1 has none, models.py:114) */
+  const float* res;    /* or NULL */
+  float* out;
+  int B, Cin, H, W, Cout, KH, KW, pad;
+  int pre_act;
+  float slope;
+  float out_scale;     /* 1/sqrt(2) for the ResBlk merge (models.py:137), else 1 */
+} st2_conv2d_args;
+int st2_conv2d(const st2_conv2d_args* a, void* stream);
+/* LearnedDownSample('half') (models.py:37-38): depthwise 3x3, stride 2, padding 1; w = st2_spectral_norm_fold output
+ * for weight_orig [C,1,3,3] (layout [9][C]); out [B,C,(H-1)/2+1,(W-1)/2+1]. */
+int st2_dwconv3x3_s2(const float* x, const float* w, const float* bias, float* out, int B, int C, int H, int W, void* stream);
+/* DownSample('half') (models.py:73-78): x [BC,H,W] -> [BC, H/2, (W+1)/2]; an odd W repeats its last column first. */
+int st2_avgpool_half(const float* x, float* out, int BC, int H, int W, void* stream);
+/* AdaptiveAvgPool2d(1) + LeakyReLU (models.py:153-154): x [rows, hw] -> out [rows]. */
+int st2_mean_hw_lrelu(const float* x, float* out, int rows, int hw, float slope, void* stream);
+/* torchaudio MelSpectrogram(n_fft 2048, win 1200, hop 300) framing: frames[(b*F+f), m] = wave[b, reflect(f*hop - win/2 + m)] * window[m],
+ * F = 1 + L/hop (center=True, reflect padding, window centred in the n_fft frame).  The DFT and the HTK filterbank are two
+ * st2_linear GEMMs; st2_mel_power squares the [re | im] halves in between; st2_logmel finishes with
+ * out[b,m,f] = (log(eps + mel) - mean) / std  (preprocess(), notebook cell 5). */
+int st2_mel_frames(const float* wave, const float* window, int B, int L, int win, int hop, int n_fft, float* frames, void* stream);
+int st2_mel_power(const float* y /* [rows, 2*nf] */, int rows, int nf, float* p /* [rows, nf] */, void* stream);
+int st2_logmel(const float* mel /* [B*F, M] */, int B, int F, int M, float eps, float mean, float stdv, float* out /* [B,M,F] */,
+               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,14 @@ class ConvArgs(C.Structure):
     ]
 
 
+class Conv2dArgs(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("wt", _vp), ("bias", _vp), ("res", _vp), ("out", _vp),
+        ("B", _i), ("Cin", _i), ("H", _i), ("W", _i), ("Cout", _i), ("KH", _i), ("KW", _i), ("pad", _i),
+        ("pre_act", _i), ("slope", _f), ("out_scale", _f),
+    ]
+
+
 class RowsArgs(C.Structure):
     _fields_ = [
         ("h_in", _vp), ("h_in_ld", _ll),
@@ -91,6 +99,14 @@ SIGNATURES = {
     "st2_sine_source": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_ulonglong, C.c_ulonglong, _vp, _vp],
     "st2_randn": [_vp, _ll, C.c_ulonglong, C.c_ulonglong, _vp, _vp],
     "st2_rng_advance": [_vp, _vp],
+    "st2_spectral_norm_fold": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "st2_conv2d": [C.POINTER(Conv2dArgs), _vp],
+    "st2_dwconv3x3_s2": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "st2_avgpool_half": [_vp, _vp, _i, _i, _i, _vp],
+    "st2_mean_hw_lrelu": [_vp, _vp, _i, _i, _f, _vp],
+    "st2_mel_frames": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp],
+    "st2_mel_power": [_vp, _i, _i, _vp, _vp],
+    "st2_logmel": [_vp, _i, _i, _i, _f, _f, _f, _vp, _vp],
     "st2_stft20": [_vp, _i, _i, _vp, _vp],
     "st2_istft20_expsin": [_vp, _i, _i, _vp, _vp],
 }

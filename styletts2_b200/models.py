@@ -1,8 +1,8 @@
 """build_model(...) with the reference's signature and container keys (models.py:614-694).
 
-Only the inference hot path is built from kernels; the training-only members of the
-reference's Munch (style encoders, discriminators, aligner, pitch extractor) are outside the scope
-table and are returned as nn.Identity() placeholders so notebook code that iterates over the
+The inference hot path (SURVEY.md section 8 a-e) and the reference-style encoders (row f2) are built from kernels;
+the training-only members of the reference's Munch (discriminators, aligner, pitch extractor) are outside the
+scope table and are returned as nn.Identity() placeholders so notebook code that iterates over the
 container (`[model[k].eval() for k in model]`) keeps working.
 """
 from __future__ import annotations
@@ -15,6 +15,7 @@ from .modules import Decoder, Linear, ProsodyPredictor, TextEncoder
 from .synthetic import keyed_state_dict
 
 HOT_MODULES = ["bert_encoder", "predictor", "decoder", "text_encoder", "diffusion"]
+STYLE_MODULES = ["style_encoder", "predictor_encoder"]      # compute_style
 
 
 class Munch(dict):
@@ -78,16 +79,20 @@ def build_model(args, text_aligner=None, pitch_extractor=None, bert=None):
     diffusion.diffusion.net = transformer
     diffusion.unet = transformer
     ident = nn.Identity
+    from .style import StyleEncoder   # models.py:639-640
+    style_encoder = StyleEncoder(dim_in=args.dim_in, style_dim=args.style_dim, max_conv_dim=args.hidden_dim)
+    predictor_encoder = StyleEncoder(dim_in=args.dim_in, style_dim=args.style_dim, max_conv_dim=args.hidden_dim)
     return Munch(bert=bert, bert_encoder=Linear(bert.config.hidden_size, args.hidden_dim), predictor=predictor, decoder=decoder,
-                 text_encoder=text_encoder, predictor_encoder=ident(), style_encoder=ident(), diffusion=diffusion,
+                 text_encoder=text_encoder, predictor_encoder=predictor_encoder, style_encoder=style_encoder, diffusion=diffusion,
                  text_aligner=text_aligner if text_aligner is not None else ident(),
                  pitch_extractor=pitch_extractor if pitch_extractor is not None else ident(), mpd=ident(), msd=ident(), wd=ident())
 
 
-def load_keyed_weights(model, seed: int = 0, voiced: bool = True):
-    """Deterministic synthetic weights (styletts2_b200/synthetic.py) into every hot-path module."""
+def load_keyed_weights(model, seed: int = 0, voiced: bool = True, modules=None):
+    """Deterministic synthetic weights (styletts2_b200/synthetic.py) into every hot-path module
+    (modules=HOT_MODULES + STYLE_MODULES also fills the reference-style encoders)."""
     sds = {}
-    for k in HOT_MODULES:
+    for k in (modules or HOT_MODULES):
         shapes = {n: tuple(v.shape) for n, v in model[k].state_dict().items()}
         sd = keyed_state_dict(shapes, k, seed=seed, voiced=voiced)
         model[k].load_state_dict(sd)

@@ -461,3 +461,79 @@ def kdiff_combine(out, out_masked, scale_):
     """classifier-free guidance: out_masked + (out - out_masked) * scale (modules.py:420-423)"""
     d = axpby(out, 1.0, out_masked, -1.0)
     return axpby(out_masked, 1.0, d, scale_)
+
+
+# ------------------------------------------------------------------ reference-style path (SURVEY 8 f2)
+def spectral_norm_fold(weight_orig, u, v):
+    """eval-mode spectral_norm weight in the conv2d kernel layout [Cin/groups*KH*KW][Cout]; returns (wt, sigma[1])."""
+    w = weight_orig.detach().contiguous()
+    cout = w.shape[0]
+    n = w.numel() // cout
+    wt = empty(n, cout, device=w.device)
+    sigma = empty(1, device=w.device)
+    L.call("st2_spectral_norm_fold", ptr(w), ptr(u.contiguous()), ptr(v.contiguous()), cout, n, ptr(wt), ptr(sigma), stream_ptr())
+    return wt, sigma
+
+
+def conv2d(x, wt, bias, *, cout, kh, kw, pad, pre_act=False, slope=0.2, res=None, out_scale=1.0):
+    from .lib import Conv2dArgs
+    x = x.contiguous()
+    B, Cin, H, W = x.shape
+    Ho, Wo = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
+    out = empty(B, cout, Ho, Wo, device=x.device)
+    if res is not None:
+        assert res.shape == out.shape and res.is_contiguous()
+    a = Conv2dArgs()
+    a.x, a.wt, a.bias, a.res, a.out = ptr(x), ptr(wt), ptr(bias), ptr(res), ptr(out)
+    a.B, a.Cin, a.H, a.W, a.Cout, a.KH, a.KW, a.pad = B, Cin, H, W, cout, kh, kw, pad
+    a.pre_act, a.slope, a.out_scale = int(bool(pre_act)), float(slope), float(out_scale)
+    L.call("st2_conv2d", C.byref(a), stream_ptr())
+    return out
+
+
+def dwconv3x3_s2(x, wt, bias):
+    x = x.contiguous()
+    B, Cc, H, W = x.shape
+    out = empty(B, Cc, (H - 1) // 2 + 1, (W - 1) // 2 + 1, device=x.device)
+    L.call("st2_dwconv3x3_s2", ptr(x), ptr(wt), ptr(bias), ptr(out), B, Cc, H, W, stream_ptr())
+    return out
+
+
+def avgpool_half(x):
+    x = x.contiguous()
+    B, Cc, H, W = x.shape
+    out = empty(B, Cc, H // 2, (W + 1) // 2, device=x.device)
+    L.call("st2_avgpool_half", ptr(x), ptr(out), B * Cc, H, W, stream_ptr())
+    return out
+
+
+def mean_hw_lrelu(x, slope=0.2):
+    x = x.contiguous()
+    B, Cc, H, W = x.shape
+    out = empty(B, Cc, device=x.device)
+    L.call("st2_mean_hw_lrelu", ptr(x), ptr(out), B * Cc, H * W, float(slope), stream_ptr())
+    return out
+
+
+def mel_frames(wave, window, hop, n_fft):
+    wave = wave.contiguous()
+    B, Ln = wave.shape
+    win = window.numel()
+    F = 1 + Ln // hop
+    frames = empty(B * F, win, device=wave.device)
+    L.call("st2_mel_frames", ptr(wave), ptr(window), B, Ln, win, hop, n_fft, ptr(frames), stream_ptr())
+    return frames, F
+
+
+def mel_power(y, nf):
+    rows = y.shape[0]
+    p = empty(rows, nf, device=y.device)
+    L.call("st2_mel_power", ptr(y), rows, nf, ptr(p), stream_ptr())
+    return p
+
+
+def logmel(mel, B, F, eps, mean, std):
+    M = mel.shape[1]
+    out = empty(B, M, F, device=mel.device)
+    L.call("st2_logmel", ptr(mel), B, F, M, float(eps), float(mean), float(std), ptr(out), stream_ptr())
+    return out

@@ -68,6 +68,20 @@ def keyed_state_dict(shapes: Dict[str, Tuple[int, ...]], prefix: str = "", seed:
             v = out[k[: -len("weight_g")] + "weight_v"]
             nrm = v.flatten(1).norm(dim=1).view(out[k].shape)
             out[k] = out[k] * nrm
+    for k in list(out):
+        if k.endswith(".weight_orig"):
+            # spectral_norm buffers (models.py:139-164 StyleEncoder): a trained checkpoint stores the converged
+            # power-iteration vectors, so sigma = u.(W v) is the top singular value; reproduce that here
+            base = k[: -len("weight_orig")]
+            W = out[k].flatten(1).double()
+            v = out[base + "weight_v"].double()
+            v = v / v.norm().clamp_min(1e-12)
+            for _ in range(12):
+                u = W @ v
+                u = u / u.norm().clamp_min(1e-12)
+                v = W.t() @ u
+                v = v / v.norm().clamp_min(1e-12)
+            out[base + "weight_u"], out[base + "weight_v"] = u.float(), v.float()
     if voiced and prefix == "predictor" and "F0_proj.weight" in out:
         # random nets predict F0 ~ 0 (everything unvoiced); bias the projection so the
         # harmonic source (SineGen) is exercised with voiced and unvoiced spans.
@@ -79,6 +93,22 @@ def keyed_state_dict(shapes: Dict[str, Tuple[int, ...]], prefix: str = "", seed:
         out["duration_proj.linear_layer.weight"] = out["duration_proj.linear_layer.weight"] * 10.0
         out["duration_proj.linear_layer.bias"] = out["duration_proj.linear_layer.bias"] * 10.0 - 2.0
     return out
+
+
+def synthetic_wave(B: int, samples: int, seed: int = 0) -> torch.Tensor:
+    """Reference-clip stand-in [B, samples] at 24 kHz: a few harmonics of a gliding pitch plus a noise floor
+    (every mel band carries energy, as in recorded speech)."""
+    g = _gen("wave", seed)
+    t = torch.arange(samples, dtype=torch.float64).unsqueeze(0) / 24000.0
+    f0 = 110.0 + 120.0 * torch.rand(B, 1, generator=g).double()
+    glide = 1.0 + 0.2 * torch.sin(2 * torch.pi * (0.7 + torch.rand(B, 1, generator=g).double()) * t)
+    phase = 2 * torch.pi * torch.cumsum(f0 * glide, dim=1) / 24000.0
+    wave = torch.zeros(B, samples, dtype=torch.float64)
+    for h in range(1, 9):
+        wave += (0.25 / h) * torch.sin(h * phase + 6.28 * torch.rand(B, 1, generator=g).double())
+    env = 0.6 + 0.4 * torch.sin(2 * torch.pi * 3.1 * t + 6.28 * torch.rand(B, 1, generator=g).double())
+    wave = wave * env + 0.02 * torch.randn(B, samples, generator=g).double()
+    return wave.float()
 
 
 def synthetic_f0(B: int, frames: int, seed: int = 0) -> torch.Tensor:
