@@ -191,7 +191,13 @@ int st2_embedding_sum_rows(const long long* tokens, const float* word, const flo
  * gx [B*L, 8H] = x W_ih^T + b_ih + b_hh for (fwd | bwd); whh [2][4H][H]; out element
  * (b,t,dir*H+j) at out + b*o_bs + t*o_ts + (dir*H+j)*o_cs.  lengths (int32 [B]) or NULL gives
  * pack_padded_sequence semantics (backward pass starts at lengths[b]-1; padded steps = 0).
- * work: >= 6*B*H + 64 floats of scratch. */
+ * work: >= 6*B*H + 64 floats of scratch.
+ * H == 256 (every LSTM of the reference configs) runs on 8-CTA clusters with DSMEM exchange; st2_debug_lstm_cluster(0)
+ * forces the cooperative-launch kernel used for other sizes (testing). */
+int st2_debug_lstm_cluster(int enable);
+/* Profiling aid (like st2_debug_set_trace): device buffer of 8 int64 <- per-phase cycle sums of CTA 0 / thread 0 of the
+ * cluster LSTM kernel {wait, fma, reduce, gates, push, steps}; NULL disables. */
+int st2_debug_lstm_trace(void* buf);
 int st2_lstm_bidir(const float* gx, const float* whh, float* out, long long o_bs, long long o_ts, long long o_cs,
                    const int* lengths, int B, int L, int H, float* work, void* stream);
 

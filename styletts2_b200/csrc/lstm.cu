@@ -215,14 +215,277 @@ __global__ void __launch_bounds__(LSTM_UT* LSTM_BT) lstm_persistent_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// v3 (H == 256): thread-block clusters + distributed shared memory.  One cluster of 8 CTAs owns
+// (direction, group of BG utterances): CTA r keeps the W_hh rows of hidden units [32r, 32r+32) x 4 gates
+// entirely in REGISTERS (64 weights per thread: unit u x 16-way k-slice) and the previous hidden vectors
+// of its utterances (BG x 256, double-buffered) in shared memory.  After each step the 32 new h values
+// of a CTA go straight into the shared memory of all 8 CTAs with st.async (remote store that also
+// completes bytes on the destination CTA's mbarrier), so the only synchronisation on the serial chain is
+// a local mbarrier wait: no global-memory round trip, no device-wide or cluster-wide barrier per step.
+// (Measured alternatives: barrier.cluster per step 4.3 us/step, staged cp.async.bulk rows 4.7 us/step,
+// st.async 3.7 us/step at B=32; the cooperative-launch kernel with an L2 barrier was 8.8 us/step.)
+// Step cost = BG*64 FMAs/thread + a 15-shuffle transpose-reduce + gate math + one DSMEM hop (~215 cycles).
+// Utterances are independent, so groups never synchronise with each other (B=32 -> 2 x 8 clusters = 128 SMs).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+  return remote;
+}
+// remote 4-byte store that completes 4 tx-bytes on the mbarrier of the SAME destination CTA
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_mbar)
+               : "memory");
+}
+__device__ long long* g_lstm_trace = nullptr;   // [8] cycle sums of CTA 0 / thread 0 (st2_debug_lstm_trace)
+__device__ __forceinline__ void lc_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lc_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+constexpr int LC_H = 256, LC_CTAS = 8, LC_THREADS = 512, LC_GMAX = 8;
+
+// BG utterances per pass (1..4), `npass` (1 or 2) passes per step: a cluster serves up to 8 utterances so that all
+// clusters of a call are co-resident (a B200 holds ~15 clusters of 8 CTAs; a second wave would double the time).
+template <int BG>
+__global__ void __cluster_dims__(LC_CTAS, 1, 1) __launch_bounds__(LC_THREADS, 1)
+    lstm_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ whh, float* __restrict__ out, long long o_bs,
+                        long long o_ts, long long o_cs, const int* __restrict__ lengths, int B, int L, int npass, int gsize) {
+  constexpr int H = LC_H;
+  __shared__ __align__(16) float hs[2][LC_GMAX][H];
+  __shared__ __align__(8) unsigned long long full_bar[2];   // full_bar[b]: buffer b holds the complete h of a step
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = lane & 15;                    // k-slice: float4 columns {s, 16+s, 32+s, 48+s}
+  const int u = warp * 2 + (lane >> 4);       // hidden unit inside this CTA
+  const uint32_t rank = cluster_ctarank();
+  const int ci = blockIdx.x / LC_CTAS;
+  const int dir = ci & 1, grp = ci >> 1;
+  const int j = (int)rank * 32 + u;
+  const int b0 = grp * gsize;   // gsize <= BG * npass utterances per cluster
+  const int nlive = min(gsize, B - b0);
+  const uint32_t fill_bytes = (uint32_t)nlive * H * 4u;     // 8 CTAs x 32 units x nlive utterances x 4 B
+
+  // W_hh rows of unit j, 4 gates, this thread's 16 k's, as (even k, odd k) pairs for the packed FFMA2 pipe
+  float2 w[4][8];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4* wr = reinterpret_cast<const float4*>(whh + ((long long)(dir * 4 + g) * H + j) * H);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = __ldg(wr + q * 16 + s);
+      w[g][q * 2 + 0] = make_float2(v.x, v.y);
+      w[g][q * 2 + 1] = make_float2(v.z, v.w);
+    }
+  }
+  for (int i = tid; i < 2 * LC_GMAX * H; i += LC_THREADS) (&hs[0][0][0])[i] = 0.f;
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&full_bar[0]);
+  if (tid == 0) {
+    lc_mbar_init(bar0, 1);
+    lc_mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  // after the transpose-reduce, lane gl = bb*4 + gate of each 16-lane half holds that pre-activation sum: every lane
+  // applies its own gate non-linearity (branch-free: sigma(x) = 1/(1+e^-x), tanh(x) = 2/(1+e^-2x) - 1), then the
+  // gate-0 lane of each utterance gathers f, g, o from its neighbours and finishes the cell.
+  const int gl = lane & 15;
+  const int bbl = gl >> 2, gate = gl & 3;
+  const float act_k = gate == 2 ? 2.f : 1.f, act_b = gate == 2 ? -1.f : 0.f;
+  bool valid[2];
+  int len[2];
+  const float* gxl[2];
+  float c[2] = {0.f, 0.f};
+  float nx[2] = {0.f, 0.f};   // this lane's gate pre-activation input of the coming step (fetched one step ahead)
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int ub = p * BG + bbl;
+    const int b = b0 + ub;
+    valid[p] = p < npass && bbl < BG && ub < gsize && b < B;
+    len[p] = L;
+    if (valid[p] && lengths) len[p] = lengths[b];
+    gxl[p] = gx + (long long)(valid[p] ? b : 0) * L * (8 * H) + (long long)dir * 4 * H + gate * H + j;
+    if (valid[p] && len[p] > 0) nx[p] = __ldg(gxl[p] + (long long)(dir == 0 ? 0 : len[p] - 1) * (8 * H));
+  }
+  long long* trace = (blockIdx.x == 0 && tid == 0) ? g_lstm_trace : nullptr;
+  long long tr[5] = {0, 0, 0, 0, 0};
+  cluster_barrier();  // buffers zeroed and barriers initialised in every CTA before any remote store may land
+
+  for (int step = 0; step < L; ++step) {
+    const int cur = step & 1;
+    if (tid == 0) lc_mbar_expect_tx(bar0 + 8 * (cur ^ 1), fill_bytes);   // arm this step's fill of the other buffer
+    float gxv[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      gxv[p] = nx[p];
+      if (valid[p] && step + 1 < len[p]) nx[p] = __ldg(gxl[p] + (long long)(dir == 0 ? step + 1 : len[p] - 2 - step) * (8 * H));
+    }
+    long long tc = trace ? clock64() : 0;
+    if (step > 0) lc_mbar_wait(bar0 + 8 * cur, (uint32_t)(((step - 1) >> 1) & 1));
+    if (trace) { const long long n = clock64(); tr[0] += n - tc; tc = n; }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (p < npass) {
+        float2 acc[BG][4];
+#pragma unroll
+        for (int bb = 0; bb < BG; ++bb)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) acc[bb][g] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int bb = 0; bb < BG; ++bb) {
+          const float4* hr = reinterpret_cast<const float4*>(&hs[cur][p * BG + bb][0]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 hv = hr[q * 16 + s];
+            const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              acc[bb][g] = __ffma2_rn(h01, w[g][q * 2 + 0], acc[bb][g]);
+              acc[bb][g] = __ffma2_rn(h23, w[g][q * 2 + 1], acc[bb][g]);
+            }
+          }
+        }
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (i >> 2) < BG ? acc[(i >> 2) < BG ? (i >> 2) : 0][i & 3].x + acc[(i >> 2) < BG ? (i >> 2) : 0][i & 3].y : 0.f;
+        if (trace) { const long long n = clock64(); tr[1] += n - tc; tc = n; }
+        // transpose-reduce over the 16 k-slices: 8+4+2+1 shuffles leave value #(lane&15) on each lane
+#define ST2_RED(NV, OFF)                                                        \
+  {                                                                             \
+    const bool up = (lane & OFF) != 0;                                          \
+    _Pragma("unroll") for (int i = 0; i < NV / 2; ++i) {                        \
+      const float send = up ? v[i] : v[i + NV / 2];                             \
+      const float keep = up ? v[i + NV / 2] : v[i];                             \
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);                    \
+    }                                                                           \
+  }
+        ST2_RED(16, 8)
+        ST2_RED(8, 4)
+        ST2_RED(4, 2)
+        ST2_RED(2, 1)
+#undef ST2_RED
+        if (trace) { const long long n = clock64(); tr[2] += n - tc; tc = n; }
+        const float x = v[0] + gxv[p];
+        const float a = __fdiv_rn(act_k, 1.0f + expf(-act_k * x)) + act_b;
+        const float af = __shfl_down_sync(0xffffffffu, a, 1);
+        const float ag = __shfl_down_sync(0xffffffffu, a, 2);
+        const float ao = __shfl_down_sync(0xffffffffu, a, 3);
+        if (gate == 0 && valid[p]) {
+          const int ub = p * BG + bbl;
+          const bool act = step < len[p];
+          float hnew;
+          if (!act) {
+            hnew = hs[cur][ub][j];   // pack_padded_sequence: state frozen past the utterance's length
+          } else {
+            c[p] = af * c[p] + a * ag;
+            hnew = ao * (__fdiv_rn(2.0f, 1.0f + expf(-2.0f * c[p])) - 1.0f);
+          }
+          if (trace) { const long long n = clock64(); tr[3] += n - tc; tc = n; }
+          const uint32_t laddr = (uint32_t)__cvta_generic_to_shared(&hs[cur ^ 1][ub][j]);
+          const uint32_t lbar = bar0 + 8 * (cur ^ 1);
+#pragma unroll
+          for (uint32_t r = 0; r < (uint32_t)LC_CTAS; ++r) st_async_f32(mapa_u32(laddr, r), hnew, mapa_u32(lbar, r));
+          if (act) {
+            const int t = dir == 0 ? step : (len[p] - 1 - step);
+            out[(long long)(b0 + ub) * o_bs + (long long)t * o_ts + (long long)(dir * H + j) * o_cs] = hnew;
+          }
+          if (trace) { const long long n = clock64(); tr[4] += n - tc; tc = n; }
+        }
+      }
+    }
+  }
+  if (trace) {
+    for (int i = 0; i < 5; ++i) trace[i] = tr[i];
+    trace[5] = L;
+  }
+  // drain: the last step's rows have landed here (so every copy INTO this CTA is complete), then meet the peers so
+  // that every store OUT of this CTA has completed at its destination before any CTA of the cluster retires
+  lc_mbar_wait(bar0 + 8 * (L & 1), (uint32_t)(((L - 1) >> 1) & 1));
+  cluster_barrier();
+}
+
 }  // namespace st2
 
 using namespace st2;
+
+static int g_lstm_cluster = 1;
+// testing / A-B hook: 0 selects the cooperative-launch kernel for every shape
+// profiling aid: device buffer of 8 int64 receiving, for CTA 0 / thread 0 of the cluster kernel, the cycle sums of
+// {mbarrier wait, h loads + FMAs, transpose-reduce, gate math, remote stores} and the step count; NULL disables
+extern "C" int st2_debug_lstm_trace(void* buf) {
+  long long* p = (long long*)buf;
+  cudaError_t e = cudaMemcpyToSymbol(g_lstm_trace, &p, sizeof(p));
+  if (e != cudaSuccess) { set_error("st2_debug_lstm_trace", e); return (int)e; }
+  return 0;
+}
+extern "C" int st2_debug_lstm_cluster(int enable) {
+  g_lstm_cluster = enable;
+  return 0;
+}
 
 extern "C" int st2_lstm_bidir(const float* gx, const float* whh, float* out, long long o_bs, long long o_ts, long long o_cs,
                               const int* lengths, int B, int L, int H, float* work, void* stream) {
   ST2_REQUIRE(gx && whh && out && work && B > 0 && L > 0 && H > 0 && H % 4 == 0, "st2_lstm_bidir", "bad args");
   cudaStream_t st = (cudaStream_t)stream;
+  if (H == LC_H && g_lstm_cluster) {
+    // how many 8-CTA clusters the device holds at once (GPC geometry: ~15 on a B200); a second wave would double the time
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(LC_CTAS * 16);
+      cfg.blockDim = dim3(LC_THREADS);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = LC_CTAS;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, lstm_cluster_kernel<4>, &cfg) != cudaSuccess || nc < 2) {
+        cudaGetLastError();
+        nc = 8;
+      }
+      max_clusters = nc;
+    }
+    const int groups_fit = max_clusters / 2 > 0 ? max_clusters / 2 : 1;   // two directions per utterance group
+    int gsize = cdiv(B, groups_fit);
+    if (gsize > LC_GMAX) gsize = LC_GMAX;                                  // larger batches run in waves of co-resident clusters
+    const int npass = gsize > 4 ? 2 : 1;
+    const int bg = cdiv(gsize, npass);
+    const int groups = cdiv(B, gsize);
+    dim3 grid(LC_CTAS * 2 * groups);
+    if (bg == 1) lstm_cluster_kernel<1><<<grid, LC_THREADS, 0, st>>>(gx, whh, out, o_bs, o_ts, o_cs, lengths, B, L, npass, gsize);
+    else if (bg == 2) lstm_cluster_kernel<2><<<grid, LC_THREADS, 0, st>>>(gx, whh, out, o_bs, o_ts, o_cs, lengths, B, L, npass, gsize);
+    else if (bg == 3) lstm_cluster_kernel<3><<<grid, LC_THREADS, 0, st>>>(gx, whh, out, o_bs, o_ts, o_cs, lengths, B, L, npass, gsize);
+    else lstm_cluster_kernel<4><<<grid, LC_THREADS, 0, st>>>(gx, whh, out, o_bs, o_ts, o_cs, lengths, B, L, npass, gsize);
+    ++g_launches;
+    ST2_CHECK_LAUNCH("st2_lstm_bidir (cluster)");
+    return 0;
+  }
   const size_t n = (size_t)2 * B * H;
   float* h0 = work;
   float* h1 = work + n;

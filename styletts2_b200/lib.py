@@ -99,6 +99,8 @@ SIGNATURES = {
     "st2_sine_source": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_ulonglong, C.c_ulonglong, _vp, _vp],
     "st2_randn": [_vp, _ll, C.c_ulonglong, C.c_ulonglong, _vp, _vp],
     "st2_rng_advance": [_vp, _vp],
+    "st2_debug_lstm_cluster": [_i],
+    "st2_debug_lstm_trace": [_vp],
     "st2_spectral_norm_fold": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "st2_conv2d": [C.POINTER(Conv2dArgs), _vp],
     "st2_dwconv3x3_s2": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

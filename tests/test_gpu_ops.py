@@ -250,6 +250,36 @@ def test_lstm_bidir(ragged):
         assert float(y[1, 9:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("B", [1, 3, 8, 13, 32, 37])
+def test_lstm_cluster_kernel_h256(B):
+    """H=256 (the size every LSTM of the reference has) takes the 8-CTA cluster / DSMEM kernel: check it against the
+    oracle biLSTM and against the cooperative-launch kernel on the same inputs, ragged lengths included."""
+    from styletts2_b200 import lib
+    from styletts2_b200.modules import LSTM
+    Lr, In, H = 41, 48, 256
+    m = LSTM(In, H).to(dev())
+    sd = {"l." + k: v.detach().cpu() for k, v in m.state_dict().items()}
+    x = rnd(B, Lr, In, seed=B)
+    g = torch.Generator().manual_seed(B)
+    lens = torch.randint(1, Lr + 1, (B,), generator=g)
+    lens[0] = Lr
+    ref = O.bilstm(x, sd, "l", lens)
+    li = lens.to(dev(), torch.int32)
+    y, _ = m(x.to(dev()), li)
+    lib.call("st2_debug_lstm_cluster", 0)
+    try:
+        y_coop, _ = m(x.to(dev()), li)
+    finally:
+        lib.call("st2_debug_lstm_cluster", 1)
+    assert rel(y[:, :ref.shape[1]], ref) < 2e-5, rel(y[:, :ref.shape[1]], ref)
+    assert rel(y, y_coop) < 1e-5
+    for b in range(B):
+        if int(lens[b]) < Lr:
+            assert float(y[b, int(lens[b]):].abs().max()) == 0.0
+    y2, _ = m(x.to(dev()), None)                      # unpadded path
+    assert rel(y2, O.bilstm(x, sd, "l", None)) < 2e-5
+
+
 def test_sine_source_matches_reference_arithmetic():
     """fp64 phase accumulation + PyTorch interpolation rule: |diff| <= 1e-6 on a tanh-bounded signal even
     though the instantaneous phase is ~1e4..1e5 rad."""
