@@ -233,6 +233,15 @@ def run_ours(args):
         for (n0_, e0_), (n1_, e1_) in zip(mk[:-1], mk[1:]):
             stages[n1_] = e0_.elapsed_time(e1_)
         dec_ms = stages.get("decoder", 0.0)
+    if args.dump_launches and rank == 0:
+        agg = {}
+        for name_, f_, b_, e0_, e1_ in prof:
+            r_ = agg.setdefault(name_, [0, 0.0, 0.0])
+            r_[0] += 1; r_[1] += e0_.elapsed_time(e1_); r_[2] += f_
+        rows_ = [dict(launch=k_, n=v_[0], ms=round(v_[1], 4), fp32_tflops=round(v_[2] / (v_[1] / 1e3) / 1e12, 1),
+                      executed_bf16_tflops=round(3 * v_[2] / (v_[1] / 1e3) / 1e12, 1)) for k_, v_ in sorted(agg.items(), key=lambda kv: -kv[1][1])]
+        with open(args.dump_launches, "w") as f_:
+            json.dump(rows_, f_, indent=1)
     tc_ms = sum(e0_.elapsed_time(e1_) for _, _, _, e0_, e1_ in prof)
     tc_flops = sum(f for _, f, _, _, _ in prof)
     tc_bytes = sum(b_ for _, _, b_, _, _ in prof)
@@ -328,6 +337,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-graph", dest="graph", action="store_false", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--dump-launches", default=None, help="write the per-shape table of tensor-core conv launches (CUDA events, eager pass) to this JSON file")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only (ncu): device-resident loop, no JSON contract line")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -134,7 +134,7 @@ def conv1d(x, wt, bias=None, *, K, stride=1, dil=1, pad=0, pre=None, pre_act=ACT
         if PROFILE is not None:
             e1.record()
             nbytes = 4.0 * B * Lout * (Cin + Cout * (2 if res is not None else 1) + (Cout if accum_mode else 0))
-            PROFILE.append(("conv1d_tc", 2.0 * B * Cin * Cout * K * Lout, nbytes, e0, e1))
+            PROFILE.append((f"conv1d_tc ci{Cin} co{Cout} k{K} d{dil} L{Lout} B{B}", 2.0 * B * Cin * Cout * K * Lout, nbytes, e0, e1))
     else:
         L.call("st2_conv1d", C.byref(a), stream_ptr())
     return out, stats
