@@ -174,6 +174,14 @@ long long st2_linear_tc_weight_bytes(int Nf, int K);
 int st2_linear_tc_weight_layout(const float* w, void* out, int Nf, int K, void* stream);
 int st2_linear_tc(const float* A, long long lda, const void* wtc, const float* bias, const float* R, long long ldr, float* C,
                   long long ldc, int M, int Nf, int K, int act, void* stream);
+/* Same GEMM with the activation operand pre-split ONCE into fp16 (high, low*2^11) operand stages by st2_linear_tc_split
+ * (st2_linear_tc_split_bytes bytes): both operands then reach shared memory by 1-D TMA bulk copies and no warp spends
+ * issue slots on conversion (the on-the-fly path re-splits the same rows once per 128-feature output block).
+ * planes == NULL falls back to on-the-fly splitting of A. */
+long long st2_linear_tc_split_bytes(int M, int K);
+int st2_linear_tc_split(const float* A, long long lda, int M, int K, void* planes, void* stream);
+int st2_linear_tc_pre(const float* A, long long lda, const void* planes, const void* wtc, const float* bias, const float* R,
+                      long long ldr, float* C, long long ldc, int M, int Nf, int K, int act, void* stream);
 
 /* Multi-head attention without mask (modules.py:523-535): q [B*N, H*D], kv [B*N, 2*H*D]
  * (k | v), out [B*N, H*D]; softmax(q k^T * scale) v per (b,h). D must be 64. */

@@ -2,19 +2,24 @@
 //
 //   C[m, n] = act( sum_k A[m,k] * W[n,k] + bias[n] ) + R[m,n]         A,C,R row-major, W = torch Linear weight [Nf,K]
 //
-// fp32-ACCURATE on bf16 tensor cores: the predicted integer durations are downstream of the denoiser, so its
-// arithmetic must stay at fp32 accuracy.  Every operand is split into THREE bf16 planes
-// (x = p0 + p1 + p2, 24 mantissa bits) and every product is evaluated with the six MMAs whose weight is >= 2^-16:
-// p0*q0 + p0*q1 + p1*q0 + p0*q2 + p1*q1 + p2*q0, fp32 accumulation in TMEM (relative error ~2^-23).
+// fp32-ACCURATE on 16-bit tensor cores: the predicted integer durations are downstream of the denoiser, so its
+// arithmetic must stay at fp32 accuracy.  Every operand is split into TWO fp16 planes,
+// x = h + l * 2^-11 with h = fp16(x) and l = fp16((x - h) * 2^11): 22 significand bits, and the 2^11 pre-scaling keeps
+// the low plane out of fp16's subnormal range for every |x| >= 2^-14.  A product needs the three MMAs h*h, h*l, l*h
+// (l*l is 2^-22 relative); h*h accumulates in one TMEM accumulator and the two scaled correction products in a
+// second one that the epilogue folds in with an exact * 2^-11 (the first version used three bf16 planes and six
+// MMAs per product for the same accuracy: measured error equal, denoiser time halved).
+// Range: |x| must stay below fp16's 65504 (activations and weights of this model are O(1..10)); larger values
+// produce inf/NaN loudly rather than a silently wrong result.
 //
 // Mapping (same machinery as conv_tc.cu): D[128 out-features (UMMA M) x 128 tokens (UMMA N)] in TMEM (2 x 128 columns,
 // double buffered).  A operand = weight block [128 n x 16 k], B operand = activation block [128 tokens x 16 k], both
-// K-major no-swizzle "interleave" layout (16-byte rows of 8 bf16).  Weights are pre-split and pre-arranged so that
-// one K-block stage (32 features x 3 planes) is one contiguous 24 KB 1-D TMA bulk copy.  Activations are staged by
+// K-major no-swizzle "interleave" layout (16-byte rows of 8 fp16).  Weights are pre-split and pre-arranged so that
+// one K-block stage (32 features x 2 planes) is one contiguous 16 KB 1-D TMA bulk copy.  Activations are staged by
 // 8 warps (two threads per token row: 64 contiguous bytes each, software-pipelined one block ahead).  The epilogue
 // needs no transpose: TMEM lane = out-feature, so for each token column the 32 lanes write 32 consecutive floats.
 // Warp roles: warp 0 MMA issue, warp 1 TMA producer, warps 2-9 stagers, warps 10-13 epilogue; persistent CTAs.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -26,14 +31,17 @@ namespace ltc {
 constexpr int TMF = 128;   // out features per tile (UMMA M)
 constexpr int TNT = 128;   // tokens per tile (UMMA N)
 constexpr int KB = 32;     // K block (4 chunks of 8)
-constexpr int NPL = 3;     // bf16 planes per operand
-constexpr int W_STAGES = 4;
+constexpr int NPL = 2;     // fp16 planes per operand (high, low * 2^11)
+constexpr float LO_SCALE = 2048.0f, LO_UNSCALE = 1.0f / 2048.0f;
+constexpr int W_STAGES = 6;
 constexpr int W_PLANE_BYTES = 4 * TMF * 16;          // 8 KB
-constexpr int W_STAGE_BYTES = NPL * W_PLANE_BYTES;   // 24 KB
+constexpr int W_STAGE_BYTES = NPL * W_PLANE_BYTES;   // 16 KB
 constexpr int RWP = TNT + 2;                         // chunk pitch in rows (== 2 mod 8: conflict-free 128-bit stores)
 constexpr int A_PLANE_BYTES = 4 * RWP * 16;          // 8320 B
-constexpr int A_BUF_BYTES = NPL * A_PLANE_BYTES;     // 24960 B
-constexpr int A_BUFS = 3;
+constexpr int A_BUF_BYTES = NPL * A_PLANE_BYTES;     // 16640 B
+constexpr int A_BUFS = 4;
+constexpr int PRE_PLANE_BYTES = 4 * TNT * 16;         // pre-split stage: no row padding, 8 KB per plane, 16 KB per stage
+constexpr int PRE_STAGE_BYTES = NPL * PRE_PLANE_BYTES;
 constexpr int NUM_STAGERS = 256;
 constexpr int NUM_EPI = 128;
 constexpr int THREADS = 64 + NUM_STAGERS + NUM_EPI;  // 448 (14 warps -> 16-warp allocation, 128 regs)
@@ -43,7 +51,7 @@ constexpr int SM_W = 0;
 constexpr int SM_A = SM_W + W_STAGES * W_STAGE_BYTES;
 constexpr int SM_BAR = SM_A + A_BUFS * A_BUF_BYTES;
 constexpr int SM_TOTAL = SM_BAR + 256;
-constexpr int B_WFULL = 0, B_WEMPTY = 4, B_AFULL = 8, B_AEMPTY = 11, B_TFULL = 14, B_TEMPTY = 16, B_COUNT = 18;
+constexpr int B_WFULL = 0, B_WEMPTY = 6, B_AFULL = 12, B_AEMPTY = 16, B_TFULL = 20, B_TEMPTY = 22, B_COUNT = 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -103,9 +111,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 __device__ __forceinline__ uint32_t make_idesc() {
   uint32_t d = 0;
-  d |= 1u << 4;                      // D = F32
-  d |= 1u << 7;                      // A = BF16
-  d |= 1u << 10;                     // B = BF16
+  d |= 1u << 4;                      // D = F32;  A = B = F16 (format code 0 in bits 7-9 / 10-12)
   d |= (uint32_t)(TNT >> 3) << 17;   // N
   d |= (uint32_t)(TMF >> 4) << 24;   // M
   return d;
@@ -124,21 +130,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-// x0,x1 -> three packed bf16 pairs (p0, p1, p2) with x = p0 + p1 + p2 to ~2^-24
-__device__ __forceinline__ void split3(float x0, float x1, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
-  p0 = pack_bf16(x0, x1);
-  const float r0 = x0 - __uint_as_float(p0 << 16), r1 = x1 - __uint_as_float(p0 & 0xFFFF0000u);
-  p1 = pack_bf16(r0, r1);
-  const float s0 = r0 - __uint_as_float(p1 << 16), s1 = r1 - __uint_as_float(p1 & 0xFFFF0000u);
-  p2 = pack_bf16(s0, s1);
+// x0,x1 -> two packed fp16 pairs: p0 = fp16(x), p1 = fp16((x - p0) * 2^11)   (x = p0 + p1 * 2^-11 to ~2^-22 |x|)
+__device__ __forceinline__ void split2(float x0, float x1, uint32_t& p0, uint32_t& p1) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((x0 - hf.x) * LO_SCALE, (x1 - hf.y) * LO_SCALE);
+  p0 = *reinterpret_cast<const uint32_t*>(&h);
+  p1 = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 struct LinArgs {
   const float* A; long long lda;
+  const uint8_t* planes;   // pre-split activation stages (st2_linear_tc_split) or NULL: split on the fly by the stager warps
   const uint8_t* wtc;
   const float* bias;
   const float* R; long long ldr;
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * B_COUNT);
   if (tid == 0) {
     for (int i = 0; i < W_STAGES; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
-    for (int i = 0; i < A_BUFS; ++i) { mbar_init(BAR(B_AFULL + i), NUM_STAGERS); mbar_init(BAR(B_AEMPTY + i), 1); }
+    for (int i = 0; i < A_BUFS; ++i) { mbar_init(BAR(B_AFULL + i), a.planes ? 1 : NUM_STAGERS); mbar_init(BAR(B_AEMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(B_TFULL + i), 1); mbar_init(BAR(B_TEMPTY + i), NUM_EPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,15 +175,17 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
     // ================================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = make_idesc();
-      const uint32_t lbo_a = TMF * 16, lbo_b = RWP * 16;
+      const uint32_t lbo_a = TMF * 16, lbo_b = (a.planes ? TNT : RWP) * 16;
+      const uint32_t a_plane = a.planes ? (uint32_t)PRE_PLANE_BYTES : (uint32_t)A_PLANE_BYTES;
       int ws = 0, wph = 0, as = 0, aph = 0, it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         mbar_wait(BAR(B_TEMPTY + buf), ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        // Two accumulators per tile: D_hi takes only the leading products p0*q0, D_lo the five correction products
-        // (2^-8 smaller): the tensor core truncates when it adds into an accumulator, so keeping the small terms out of
-        // the big running sum cuts the accumulation error ~6x (measured 4.4e-6 -> fp32-SIMT level at K=1024).
+        // Two accumulators per tile: D_hi takes only the leading products h*h, D_lo the two correction products (kept
+        // 2^11 times larger than their true weight).  The tensor core truncates when it adds into an accumulator, so
+        // keeping the small terms out of the big running sum also cuts the accumulation error (measured with the
+        // bf16 version: 4.4e-6 -> fp32-SIMT level at K=1024).
         const uint32_t d_hi = tmem_base + (uint32_t)buf * (2 * TNT);
         const uint32_t d_lo = d_hi + TNT;
         uint32_t first = 1;
@@ -196,15 +201,12 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
 #pragma unroll
             for (int p = 0; p < NPL; ++p) {
               da[p] = make_desc(wb + p * W_PLANE_BYTES + (2 * k16) * lbo_a, lbo_a, 128);
-              db[p] = make_desc(ab + p * A_PLANE_BYTES + (2 * k16) * lbo_b, lbo_b, 128);
+              db[p] = make_desc(ab + p * a_plane + (2 * k16) * lbo_b, lbo_b, 128);
             }
             tc_mma(d_hi, da[0], db[0], idesc, first ? 0u : 1u);
             tc_mma(d_lo, da[0], db[1], idesc, first ? 0u : 1u);
             first = 0;
             tc_mma(d_lo, da[1], db[0], idesc, 1u);
-            tc_mma(d_lo, da[0], db[2], idesc, 1u);
-            tc_mma(d_lo, da[1], db[1], idesc, 1u);
-            tc_mma(d_lo, da[2], db[0], idesc, 1u);
           }
           tc_commit(BAR(B_WEMPTY + ws));
           tc_commit(BAR(B_AEMPTY + as));
@@ -237,6 +239,21 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
     const int row = st >> 1, hf = st & 1;
     const int K_ = a.K, M_ = a.M;
     int as = 0, aph = 0;
+    if (a.planes) {
+      // pre-split activations: every (token block, K block) stage is one contiguous 16 KB image of the operand buffer
+      if (st == 0) {
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+          const int tq = tile % n_tq;
+          for (int cb = 0; cb < ncb; ++cb) {
+            mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
+            mbar_expect_tx(BAR(B_AFULL + as), PRE_STAGE_BYTES);
+            bulk_g2s(sbase + SM_A + as * A_BUF_BYTES, a.planes + ((size_t)tq * ncb + cb) * PRE_STAGE_BYTES, PRE_STAGE_BYTES,
+                     BAR(B_AFULL + as));
+            if (++as == A_BUFS) { as = 0; aph ^= 1; }
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int tq = tile % n_tq;
       const int m = tq * TNT + row;
@@ -271,16 +288,15 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
 #pragma unroll
         for (int c = 0; c < 2; ++c) {  // two 8-feature chunks of this thread's 16 floats
           const float4 v0 = cur[2 * c], v1 = cur[2 * c + 1];
-          uint32_t p0[4], p1[4], p2[4];
-          split3(v0.x, v0.y, p0[0], p1[0], p2[0]);
-          split3(v0.z, v0.w, p0[1], p1[1], p2[1]);
-          split3(v1.x, v1.y, p0[2], p1[2], p2[2]);
-          split3(v1.z, v1.w, p0[3], p1[3], p2[3]);
+          uint32_t p0[4], p1[4];
+          split2(v0.x, v0.y, p0[0], p1[0]);
+          split2(v0.z, v0.w, p0[1], p1[1]);
+          split2(v1.x, v1.y, p0[2], p1[2]);
+          split2(v1.z, v1.w, p0[3], p1[3]);
           const int kc = hf * 2 + c;
           const size_t off = (size_t)(kc * RWP + row) * 16;
           *reinterpret_cast<uint4*>(base + off) = make_uint4(p0[0], p0[1], p0[2], p0[3]);
           *reinterpret_cast<uint4*>(base + A_PLANE_BYTES + off) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-          *reinterpret_cast<uint4*>(base + 2 * A_PLANE_BYTES + off) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
         }
         fence_proxy_async();
         mbar_arrive(BAR(B_AFULL + as));
@@ -311,7 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
           tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 2 * TNT + c0), v);
           tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * 2 * TNT + TNT + c0), vl);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += vl[j];
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(vl[j], LO_UNSCALE, v[j]);
         }
         float rv[32];
 #pragma unroll
@@ -342,8 +358,45 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
   }
 }
 
-// W [Nf,K] fp32 -> [n_cob][ncb][3 planes][4 kc][128 n][8 k] bf16
-__global__ void linear_tc_weight_layout_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Nf, int K, int n_cob,
+// A [M,K] fp32 (row stride lda) -> pre-split operand stages [n_tq][ncb][2 planes][4 kc][128 rows][8 k] fp16, zero padded:
+// done ONCE per activation matrix instead of once per 128-feature output block inside the GEMM
+__global__ void linear_tc_split_kernel(const float* __restrict__ A, long long lda, int M, int K, int n_tq, int ncb,
+                                       uint4* __restrict__ out) {
+  const long long total = (long long)n_tq * ncb * 4 * TNT;
+  const bool vec_ok = ((lda & 3) == 0) && ((reinterpret_cast<size_t>(A) & 15) == 0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i % TNT);
+    long long r = i / TNT;
+    const int kc = (int)(r % 4); r /= 4;
+    const int cb = (int)(r % ncb);
+    const int tq = (int)(r / ncb);
+    const int m = tq * TNT + row, k0 = cb * KB + kc * 8;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    if (m < M) {
+      const float* p = A + (long long)m * lda + k0;
+      if (vec_ok && k0 + 7 < K) {
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(p)), v1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (k0 + j < K) x[j] = __ldg(p + j);
+      }
+    }
+    uint32_t p0[4], p1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split2(x[2 * q], x[2 * q + 1], p0[q], p1[q]);
+    const long long stage = (long long)tq * ncb + cb;
+    uint4* hi = out + (stage * NPL * 4 + kc) * TNT + row;       // 16-byte units
+    hi[0] = make_uint4(p0[0], p0[1], p0[2], p0[3]);
+    hi[4 * TNT] = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+  }
+}
+
+// W [Nf,K] fp32 -> [n_cob][ncb][2 planes][4 kc][128 n][8 k] fp16
+__global__ void linear_tc_weight_layout_kernel(const float* __restrict__ w, __half* __restrict__ out, int Nf, int K, int n_cob,
                                                int ncb) {
   const long long total = (long long)n_cob * ncb * NPL * 4 * TMF * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -357,11 +410,9 @@ __global__ void linear_tc_weight_layout_kernel(const float* __restrict__ w, __nv
     const int n = cob * TMF + col, k = cb * KB + kc * 8 + j;
     float v = 0.f;
     if (n < Nf && k < K) v = w[(long long)n * K + k];
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v);
-    const float r0 = v - __bfloat162float(h0);
-    const __nv_bfloat16 h1 = __float2bfloat16_rn(r0);
-    const __nv_bfloat16 h2 = __float2bfloat16_rn(r0 - __bfloat162float(h1));
-    out[i] = pl == 0 ? h0 : (pl == 1 ? h1 : h2);
+    const __half h0 = __float2half_rn(v);
+    const __half h1 = __float2half_rn((v - __half2float(h0)) * LO_SCALE);
+    out[i] = pl == 0 ? h0 : h1;
   }
 }
 
@@ -378,17 +429,38 @@ long long st2_linear_tc_weight_bytes(int Nf, int K) {
 
 int st2_linear_tc_weight_layout(const float* w, void* out, int Nf, int K, void* stream) {
   ST2_REQUIRE(w && out && Nf > 0 && K > 0, "st2_linear_tc_weight_layout", "bad args");
-  ltc::linear_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out, Nf, K, cdiv(Nf, ltc::TMF),
+  ltc::linear_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (__half*)out, Nf, K, cdiv(Nf, ltc::TMF),
                                                                               cdiv(K, ltc::KB));
   ++g_launches;
   ST2_CHECK_LAUNCH("st2_linear_tc_weight_layout");
   return 0;
 }
 
+long long st2_linear_tc_split_bytes(int M, int K) {
+  return (long long)cdiv(M, ltc::TNT) * cdiv(K, ltc::KB) * ltc::PRE_STAGE_BYTES;
+}
+
+int st2_linear_tc_split(const float* A, long long lda, int M, int K, void* planes, void* stream) {
+  ST2_REQUIRE(A && planes && M > 0 && K > 0, "st2_linear_tc_split", "bad args");
+  const int n_tq = cdiv(M, ltc::TNT), ncb = cdiv(K, ltc::KB);
+  const long long total = (long long)n_tq * ncb * 4 * ltc::TNT;
+  const int grid = (int)((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
+  ltc::linear_tc_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, M, K, n_tq, ncb, (uint4*)planes);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_linear_tc_split");
+  return 0;
+}
+
 int st2_linear_tc(const float* A, long long lda, const void* wtc, const float* bias, const float* R, long long ldr, float* C,
                   long long ldc, int M, int Nf, int K, int act, void* stream) {
-  ST2_REQUIRE(A && wtc && C && M > 0 && Nf > 0 && K > 0, "st2_linear_tc", "bad args");
+  return st2_linear_tc_pre(A, lda, nullptr, wtc, bias, R, ldr, C, ldc, M, Nf, K, act, stream);
+}
+
+int st2_linear_tc_pre(const float* A, long long lda, const void* planes, const void* wtc, const float* bias, const float* R,
+                      long long ldr, float* C, long long ldc, int M, int Nf, int K, int act, void* stream) {
+  ST2_REQUIRE((A || planes) && wtc && C && M > 0 && Nf > 0 && K > 0, "st2_linear_tc", "bad args");
   ltc::LinArgs a;
+  a.planes = (const uint8_t*)planes;
   a.A = A; a.lda = lda; a.wtc = (const uint8_t*)wtc; a.bias = bias; a.R = R; a.ldr = ldr; a.C = C; a.ldc = ldc;
   a.M = M; a.Nf = Nf; a.K = K; a.act = act;
   const int n_tq = cdiv(M, ltc::TNT), n_cob = cdiv(Nf, ltc::TMF), ncb = cdiv(K, ltc::KB);

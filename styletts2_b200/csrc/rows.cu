@@ -152,6 +152,123 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ A
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Small-M Linear (M <= 64 rows: the per-utterance vectors of the path -- time/feature mapping MLP of the denoiser,
+// AdaLayerNorm / AdaIN style projections): a weight-streaming split-K kernel.  The 64x64-tile SGEMM above gives such a
+// shape 16 CTAs that each walk K serially (~100 us for 32x1024x1024).  Here a CTA of 8 warps owns 8 output features;
+// warp w owns the K chunks {w, w+8, ...} (128 floats per chunk: one float4 per lane, weights read exactly once,
+// coalesced) for all rows, two features at a time; row loads are issued in batches of 8 so that their latency
+// overlaps; the 2 x 32 per-lane partial sums are folded with a transpose-reduce (31 shuffles per feature), the 8
+// per-warp partials are summed in a fixed order through shared memory (deterministic) and one thread finishes each
+// (row, feature) with bias / activation / residual.
+constexpr int SM_MT = 32;   // rows per pass
+constexpr int SM_NF = 8;    // features per CTA
+constexpr int SM_NW = 8;    // warps per CTA (K slices)
+
+template <bool VEC>
+__global__ void __launch_bounds__(SM_NW * 32) linear_smallm_kernel(const float* __restrict__ A, long long a_bs, long long a_ls,
+                                                                  int a_L, const float* __restrict__ W,
+                                                                  const float* __restrict__ bias, const float* __restrict__ R,
+                                                                  long long ldr, float* __restrict__ C, long long ldc, int M, int Nf,
+                                                                  int K, int act) {
+  __shared__ float part[SM_NW][SM_NF][SM_MT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb = blockIdx.x * SM_NF;
+  constexpr int CH = VEC ? 128 : 32;     // floats of K per warp-wide step
+  for (int mt = 0; mt < M; mt += SM_MT) {
+    const int mrows = min(SM_MT, M - mt);
+    // row base pointers of this pass (rows beyond M alias the last valid row: loaded but never stored)
+    const float* rowp[SM_MT];
+#pragma unroll
+    for (int m = 0; m < SM_MT; ++m) {
+      const int mg = mt + min(m, mrows - 1);
+      const int bi = mg / a_L, l = mg - bi * a_L;
+      rowp[m] = A + (long long)bi * a_bs + (long long)l * a_ls;
+    }
+#pragma unroll 1
+    for (int fp = 0; fp < SM_NF; fp += 2) {
+      const int n0 = min(nb + fp, Nf - 1), n1 = min(nb + fp + 1, Nf - 1);
+      const float* w0 = W + (long long)n0 * K;
+      const float* w1 = W + (long long)n1 * K;
+      float acc0[SM_MT], acc1[SM_MT];
+#pragma unroll
+      for (int m = 0; m < SM_MT; ++m) { acc0[m] = 0.f; acc1[m] = 0.f; }
+      for (int k0 = warp * CH; k0 < K; k0 += SM_NW * CH) {
+        if (VEC) {
+          const int k = k0 + lane * 4;
+          if (k < K) {
+            const float4 wa = __ldg(reinterpret_cast<const float4*>(w0 + k));
+            const float4 wb = __ldg(reinterpret_cast<const float4*>(w1 + k));
+#pragma unroll
+            for (int m8 = 0; m8 < SM_MT; m8 += 8) {
+              float4 av[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) av[i] = __ldg(reinterpret_cast<const float4*>(rowp[m8 + i] + k));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float a0 = acc0[m8 + i], a1 = acc1[m8 + i];
+                a0 = fmaf(av[i].x, wa.x, a0); a0 = fmaf(av[i].y, wa.y, a0); a0 = fmaf(av[i].z, wa.z, a0); a0 = fmaf(av[i].w, wa.w, a0);
+                a1 = fmaf(av[i].x, wb.x, a1); a1 = fmaf(av[i].y, wb.y, a1); a1 = fmaf(av[i].z, wb.z, a1); a1 = fmaf(av[i].w, wb.w, a1);
+                acc0[m8 + i] = a0; acc1[m8 + i] = a1;
+              }
+            }
+          }
+        } else {
+          const int k = k0 + lane;
+          if (k < K) {
+            const float wa = __ldg(w0 + k), wb = __ldg(w1 + k);
+#pragma unroll
+            for (int m8 = 0; m8 < SM_MT; m8 += 8) {
+              float av[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) av[i] = __ldg(rowp[m8 + i] + k);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                acc0[m8 + i] = fmaf(av[i], wa, acc0[m8 + i]);
+                acc1[m8 + i] = fmaf(av[i], wb, acc1[m8 + i]);
+              }
+            }
+          }
+        }
+      }
+      // transpose-reduce over the 32 lanes: afterwards lane m holds this warp's partial sums of row (mt + m)
+#define ST2_TRED(ACC, NV, OFF)                                                  \
+  {                                                                             \
+    const bool up = (lane & OFF) != 0;                                          \
+    _Pragma("unroll") for (int i = 0; i < NV / 2; ++i) {                        \
+      const float send = up ? ACC[i] : ACC[i + NV / 2];                         \
+      const float keep = up ? ACC[i + NV / 2] : ACC[i];                         \
+      ACC[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);                  \
+    }                                                                           \
+  }
+      ST2_TRED(acc0, 32, 16) ST2_TRED(acc0, 16, 8) ST2_TRED(acc0, 8, 4) ST2_TRED(acc0, 4, 2) ST2_TRED(acc0, 2, 1)
+      ST2_TRED(acc1, 32, 16) ST2_TRED(acc1, 16, 8) ST2_TRED(acc1, 8, 4) ST2_TRED(acc1, 4, 2) ST2_TRED(acc1, 2, 1)
+#undef ST2_TRED
+      part[warp][fp][lane] = acc0[0];
+      part[warp][fp + 1][lane] = acc1[0];
+    }
+    __syncthreads();
+    {
+      const int f = threadIdx.x >> 5, m = threadIdx.x & 31;   // 256 threads = 8 features x 32 rows
+      const int n = nb + f;
+      if (n < Nf && m < mrows) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < SM_NW; ++w) v += part[w][f][m];
+        v += bias ? bias[n] : 0.f;
+        if (act == ST2_ACT_GELU) v = gelu_erf(v);
+        else if (act == ST2_ACT_TANH) v = tanhf(v);
+        else if (act == ST2_ACT_GELU_TANH) v = gelu_tanh(v);
+        const long long mg = mt + m;
+        if (R) v += R[mg * ldr + n];
+        C[mg * ldc + n] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Attention (no mask), D = 64.  CTA = 4 warps, 16 queries (4 per warp); keys streamed in chunks of
 // 32 through shared memory; lane-per-key dot products, online softmax, P V through shared memory.
@@ -275,6 +392,16 @@ int st2_mean_rows(const float* h, long long ld, int B, int N, int C, float* out,
 int st2_linear(const float* A, long long a_bs, long long a_ls, long long a_ks, int a_L, const float* W, const float* bias,
                const float* R, long long ldr, float* C, long long ldc, int M, int Nf, int K, int act, void* stream) {
   ST2_REQUIRE(A && W && C && M > 0 && Nf > 0 && K > 0 && a_L > 0, "st2_linear", "bad args");
+  if (M <= 64 && a_ks == 1) {
+    const bool vec = (K % 4 == 0) && (a_bs % 4 == 0) && (a_ls % 4 == 0) && ((reinterpret_cast<size_t>(A) & 15) == 0) &&
+                     ((reinterpret_cast<size_t>(W) & 15) == 0);
+    const int grid = cdiv(Nf, SM_NF);
+    if (vec) linear_smallm_kernel<true><<<grid, SM_NW * 32, 0, (cudaStream_t)stream>>>(A, a_bs, a_ls, a_L, W, bias, R, ldr, C, ldc, M, Nf, K, act);
+    else linear_smallm_kernel<false><<<grid, SM_NW * 32, 0, (cudaStream_t)stream>>>(A, a_bs, a_ls, a_L, W, bias, R, ldr, C, ldc, M, Nf, K, act);
+    ++g_launches;
+    ST2_CHECK_LAUNCH("st2_linear (small M)");
+    return 0;
+  }
   dim3 grid(cdiv(Nf, GBN), cdiv(M, GBM));
   linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, a_bs, a_ls, a_ks, a_L, W, bias, R, ldr, C, ldc, M, Nf, K, act);
   ++g_launches;

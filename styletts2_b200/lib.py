@@ -83,6 +83,9 @@ SIGNATURES = {
     "st2_linear_tc_weight_bytes": [_i, _i],
     "st2_linear_tc_weight_layout": [_vp, _vp, _i, _i, _vp],
     "st2_linear_tc": [_vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp],
+    "st2_linear_tc_pre": [_vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp],
+    "st2_linear_tc_split": [_vp, _ll, _i, _i, _vp, _vp],
+    "st2_linear_tc_split_bytes": [_i, _i],
     "st2_attention": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "st2_attention_ex": [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],
     "st2_embedding_sum_rows": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
@@ -113,7 +116,8 @@ SIGNATURES = {
     "st2_istft20_expsin": [_vp, _i, _i, _vp, _vp],
 }
 _RESTYPES = {"st2_last_error": C.c_char_p, "st2_launch_count": C.c_longlong, "st2_conv_tc_weight_bytes": C.c_longlong,
-             "st2_convT_tc_weight_bytes": C.c_longlong, "st2_linear_tc_weight_bytes": C.c_longlong}
+             "st2_convT_tc_weight_bytes": C.c_longlong, "st2_linear_tc_weight_bytes": C.c_longlong,
+             "st2_linear_tc_split_bytes": C.c_longlong}
 
 _lib = None
 

@@ -258,6 +258,7 @@ def _rows_view(t):
 
 
 LINEAR_TC_MIN_ROWS = 256
+LINEAR_TC_PRESPLIT = os.environ.get("ST2_LINEAR_PRESPLIT", "1") != "0"
 
 
 def linear_tc_weight_layout(W: torch.Tensor) -> torch.Tensor:
@@ -285,7 +286,14 @@ def linear(A, W, bias=None, *, act=ACT_NONE, R=None, out=None, wtc=None):
         R2, Mr, ldr = _rows_view(R)
         assert R2.data_ptr() == R.data_ptr() and Mr == M
     if wtc is not None and USE_TC and M >= LINEAR_TC_MIN_ROWS:
-        L.call("st2_linear_tc", ptr(A2), lda, ptr(wtc), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
+        if Nf > 128 and LINEAR_TC_PRESPLIT:
+            # split the activation rows into fp16 operand stages once (not once per 128-feature output block inside the GEMM)
+            planes = torch.empty(int(L.load().st2_linear_tc_split_bytes(M, K)), dtype=torch.uint8, device=A.device)
+            L.call("st2_linear_tc_split", ptr(A2), lda, M, K, ptr(planes), stream_ptr())
+            L.call("st2_linear_tc_pre", ptr(A2), lda, ptr(planes), ptr(wtc), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act,
+                   stream_ptr())
+        else:
+            L.call("st2_linear_tc", ptr(A2), lda, ptr(wtc), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
     else:
         L.call("st2_linear", ptr(A2), 0, lda, 1, M, ptr(W), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
     return out

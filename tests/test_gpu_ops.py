@@ -199,7 +199,8 @@ def test_rows_ln_plain_and_ada():
     assert rel(a.view(B, N, C), ada_ref) < 1e-5
 
 
-@pytest.mark.parametrize("shape", [(33, 257, 1024), (300, 1024, 512), (64, 640, 2048), (5, 128, 50)])
+@pytest.mark.parametrize("shape", [(33, 257, 1024), (300, 1024, 512), (64, 640, 2048), (5, 128, 50), (32, 1024, 1024), (1, 768, 7),
+                                   (40, 256, 129), (65, 512, 96)])
 def test_linear_bias_gelu_residual(shape):
     from styletts2_b200 import ops
     from styletts2_b200.lib import ACT_GELU
@@ -209,6 +210,20 @@ def test_linear_bias_gelu_residual(shape):
     ref = F.gelu(F.linear(A, W, b)) + R
     y = ops.linear(A.to(D), W.to(D), b.to(D), act=ACT_GELU, R=R.to(D))
     assert rel(y, ref) < 1e-5, rel(y, ref)
+
+
+def test_linear_small_m_strided_rows():
+    """small-M kernel on a column slice of a wider buffer (row stride > K) and writing into a slice"""
+    from styletts2_b200 import ops
+    D = dev()
+    M, K, Nf = 32, 128, 2048
+    big = rnd(M, 3 * K, seed=1)
+    W, b = rnd(Nf, K, seed=2, scale=1 / math.sqrt(K)), rnd(Nf, seed=3)
+    A = big.to(D)[:, K:2 * K]
+    out = torch.zeros(M, Nf + 64, device=D)
+    ops.linear(A, W.to(D), b.to(D), out=out[:, 64:])
+    ref = F.linear(big[:, K:2 * K], W, b)
+    assert rel(out[:, 64:], ref) < 1e-5 and float(out[:, :64].abs().max()) == 0.0
 
 
 def test_linear_conv_layout_input():
