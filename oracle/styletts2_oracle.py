@@ -515,12 +515,15 @@ def adpm2_sample(noise, sd: SD, num_steps: int, embedding, features=None, embedd
 # --------------------------------------------------------------------------- end to end glue
 def synthesize(sds: Dict[str, SD], model_cfg, tokens, input_lengths, bert_dur, noise, *,
                diffusion_steps=5, embedding_scale=1.0, ref_s=None, alpha=0.3, beta=0.7,
-               rng=None, forced_durations=None, sigma_data=0.2):
+               rng=None, forced_durations=None, sigma_data=0.2, s_prev=None, t=0.7, skip_decoder=False):
     """Batched (equal-length) version of the notebook `inference` glue
     (Demo/Inference_LJSpeech.ipynb#cell17 single-speaker; Demo/Inference_LibriTTS.ipynb#cell16
     multispeaker when ref_s is given).  `bert_dur` [B,N,768] is PL-BERT's output (an
     input producer).  rng: dict with optional 'step_noises' (list),
-    'rand_ini', 'sine_noise', 'har' (teacher-forced STFT features).  Returns a dict of every stage boundary."""
+    'rand_ini', 'sine_noise', 'har' (teacher-forced STFT features).  s_prev / t: the long-form style carry-over of
+    `LFinference` (Demo/Inference_LJSpeech.ipynb#cell29, Demo/Inference_LibriTTS.ipynb#cell42): s_pred = t*s_prev +
+    (1-t)*s_pred before the split; 's_carry' is what the notebook returns as the next s_prev.
+    Returns a dict of every stage boundary."""
     rng = rng or {}
     dec_cfg = model_cfg["decoder"]
     multispeaker = ref_s is not None
@@ -530,11 +533,15 @@ def synthesize(sds: Dict[str, SD], model_cfg, tokens, input_lengths, bert_dur, n
     s_pred = adpm2_sample(noise, sub(sds["diffusion"], "diffusion.net"), diffusion_steps, bert_dur,
                           features=ref_s, embedding_scale=embedding_scale, sigma_data=sigma_data,
                           step_noises=rng.get("step_noises")).squeeze(1)
+    if s_prev is not None:
+        s_pred = t * s_prev + (1 - t) * s_pred
     s = s_pred[:, 128:]
     ref = s_pred[:, :128]
+    s_carry = s_pred
     if multispeaker:
         ref = alpha * ref + (1 - alpha) * ref_s[:, :128]
         s = beta * s + (1 - beta) * ref_s[:, 128:]
+        s_carry = torch.cat([ref, s], dim=-1)
     pred = sds["predictor"]
     d = duration_encoder(d_en, s, input_lengths, mask, sub(pred, "text_encoder"))
     logits = duration_logits(d, pred)
@@ -549,7 +556,7 @@ def synthesize(sds: Dict[str, SD], model_cfg, tokens, input_lengths, bert_dur, n
     if dec_cfg["type"] == "hifigan":
         en, asr = shift_right_one(en), shift_right_one(asr)
     f0, n = f0n_train(en, s, pred)
-    wav = decoder(asr, f0, n, ref, sds["decoder"], dec_cfg, rng.get("rand_ini"), rng.get("sine_noise"),
-                  rng.get("har"))
+    wav = None if skip_decoder else decoder(asr, f0, n, ref, sds["decoder"], dec_cfg, rng.get("rand_ini"), rng.get("sine_noise"),
+                                            rng.get("har"))
     return dict(t_en=t_en, d_en=d_en, s_pred=s_pred, s=s, ref=ref, d=d, logits=logits, pred_dur=pred_dur,
-                en=en, asr=asr, F0=f0, N=n, wav=wav)
+                en=en, asr=asr, F0=f0, N=n, wav=wav, s_carry=s_carry)

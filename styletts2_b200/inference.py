@@ -43,13 +43,15 @@ class Synthesizer:
     @torch.no_grad()
     def synthesize(self, tokens, input_lengths, bert_dur, noise, *, diffusion_steps=5, embedding_scale=1.0, ref_s=None,
                    alpha=0.3, beta=0.7, rng: Optional[Dict] = None, forced_durations=None, pin_frames_per_token=None,
-                   return_all=False, decoder_events=None, stage_marks=None):
+                   return_all=False, decoder_events=None, stage_marks=None, s_prev=None, t=0.7):
         """tokens [B,N] i64, input_lengths [B], bert_dur [B,N,768], noise [B,1,256] (device tensors).
         rng (parity mode): 'step_noises' list of [B,1,256], 'sine_noise' [B,L,9], 'har' [B,22,F],
         'F0' / 'N' [B,2T] (teacher-forced prosody curves: the harmonic source integrates F0 into a phase
         of 1e4..1e6 rad, so waveform comparisons inject the reference's curves after checking ours).
         forced_durations [B,N] int: teacher-forced durations (after the duration kernel has run).
-        pin_frames_per_token: throughput mode of SURVEY section 8d (durations pinned so that T = N*k)."""
+        pin_frames_per_token: throughput mode of SURVEY section 8d (durations pinned so that T = N*k).
+        s_prev [B,256], t: long-form style carry-over of the notebooks' LFinference (LJSpeech cell 29, LibriTTS cell 42):
+        s_pred = t*s_prev + (1-t)*s_pred before it is split; out['s_carry'] is the value to pass as the next s_prev."""
         m = self.model
         rng = rng or {}
         dev = self.device
@@ -75,12 +77,20 @@ class Synthesizer:
             kw["features"] = ref_s
         s_pred = self.sampler(noise, **kw).reshape(B, 256)
         mark("sampler")
+        if s_prev is not None:
+            s_pred = ops.axpby(s_prev.reshape(B, 256), t, s_pred, 1 - t)
         s = s_pred[:, 128:]
         ref = s_pred[:, :128]
+        s_carry = s_pred
         if self.multispeaker:
             ref = ops.axpby(ref, alpha, ref_s[:, :128], 1 - alpha)
             s = ops.axpby(s, beta, ref_s[:, 128:], 1 - beta)
+            s_carry = None   # assembled below from the blended halves (LibriTTS cell 42: torch.cat([ref, s]))
         s, ref = s.contiguous(), ref.contiguous()
+        if s_carry is None:
+            s_carry = torch.empty(B, 256, device=dev)
+            s_carry[:, :128].copy_(ref)
+            s_carry[:, 128:].copy_(s)
         d = m.predictor.text_encoder(d_en_rows.transpose(-1, -2), s, input_lengths, mask)   # [B,N,640]
         x, _ = m.predictor.lstm(d)
         logits = m.predictor.duration_proj(x)                                     # [B,N,50]
@@ -114,7 +124,7 @@ class Synthesizer:
             ev1.record()
             decoder_events.append((ev0, ev1))
         mark("decoder")
-        out = dict(wav=wav, pred_dur=pred_dur, T=T)
+        out = dict(wav=wav, pred_dur=pred_dur, T=T, s_carry=s_carry)
         if return_all:
             out.update(t_en=t_en, d_en=d_en_rows.transpose(-1, -2), s_pred=s_pred, s=s, ref=ref, d=d, logits=logits,
                        dur_f=dur_f, en=en_rows.transpose(-1, -2), asr=asr, F0=F0, N=Ncurve)
@@ -157,6 +167,22 @@ class Synthesizer:
             st["ref_s"].copy_(ref_s, non_blocking=True)
         ent["graph"].replay()
         return ent["wav"], ent["launches"]
+
+    @torch.no_grad()
+    def LFinference(self, tokens: List[int], bert_dur, s_prev, noise=None, ref_s=None, alpha=0.3, beta=0.7, t=0.7,
+                    diffusion_steps=5, embedding_scale=1.0):
+        """Long-form step with the notebooks' conventions (LJSpeech cell 29: `alpha` there is `t` here; LibriTTS cell 42):
+        returns (numpy waveform, s_pred to pass as the next sentence's s_prev)."""
+        dev = self.device
+        tk = torch.tensor([list(tokens)], dtype=torch.long, device=dev)
+        lens = torch.tensor([tk.shape[1]], dtype=torch.long, device=dev)
+        if noise is None:
+            noise = ops.randn_like(torch.empty(1, 1, 256, device=dev))
+        out = self.synthesize(tk, lens, bert_dur.to(dev), noise.to(dev), diffusion_steps=diffusion_steps,
+                              embedding_scale=embedding_scale, ref_s=None if ref_s is None else ref_s.to(dev), alpha=alpha,
+                              beta=beta, s_prev=None if s_prev is None else s_prev.to(dev), t=t)
+        wav = out["wav"].squeeze().cpu().numpy()
+        return (wav[..., :-50] if self.multispeaker else wav), out["s_carry"]
 
     @torch.no_grad()
     def inference(self, tokens: List[int], bert_dur, noise=None, ref_s=None, alpha=0.3, beta=0.7, diffusion_steps=5,

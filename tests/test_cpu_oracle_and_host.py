@@ -140,3 +140,26 @@ def test_utterance_sharding_plan():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
         assert all(e - s == B // W for s, e in spans)
     assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def test_oracle_long_form_carry_over_properties():
+    """LFinference restatement: t=0 ignores s_prev; carrying a sentence's own unblended style back in is a fixed point
+    (single speaker); the multispeaker carry is cat([ref, s]) after the ref_s blend."""
+    case = dict(model="ljspeech", B=1, N=6, seed=3)
+    tokens, lengths, bert_dur, noise, _ = cases.e2e_inputs(case)
+    sds = oracle_sds("ljspeech")
+    cfg = cases.MODEL_CFGS["ljspeech"]
+    steps = [torch.randn(1, 1, 256, generator=torch.Generator().manual_seed(i)) for i in range(2)]
+    kw = dict(diffusion_steps=3, rng=dict(step_noises=steps), skip_decoder=True, forced_durations=torch.full((1, 6), 2.0))
+    with torch.no_grad():
+        base = O.synthesize(sds, cfg, tokens, lengths, bert_dur, noise, **kw)
+        t0 = O.synthesize(sds, cfg, tokens, lengths, bert_dur, noise, s_prev=torch.randn(1, 256), t=0.0, **kw)
+        fix = O.synthesize(sds, cfg, tokens, lengths, bert_dur, noise, s_prev=base["s_pred"], t=0.7, **kw)
+    assert torch.equal(t0["s_carry"], base["s_pred"]) and torch.equal(t0["F0"], base["F0"])
+    assert float((fix["s_carry"] - base["s_pred"]).abs().max()) < 1e-6
+    assert base["wav"] is None
+    case = dict(model="libritts", B=1, N=6, seed=4)
+    tokens, lengths, bert_dur, noise, ref_s = cases.e2e_inputs(case)
+    with torch.no_grad():
+        ms = O.synthesize(oracle_sds("libritts"), cases.MODEL_CFGS["libritts"], tokens, lengths, bert_dur, noise, ref_s=ref_s, **kw)
+    assert torch.equal(ms["s_carry"], torch.cat([ms["ref"], ms["s"]], dim=-1))

@@ -265,7 +265,7 @@ def test_lstm_bidir(ragged):
         assert float(y[1, 9:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("B", [1, 3, 8, 13, 32, 37])
+@pytest.mark.parametrize("B", [1, 3, 8, 13, 32, 37, 50, 70])
 def test_lstm_cluster_kernel_h256(B):
     """H=256 (the size every LSTM of the reference has) takes the 8-CTA cluster / DSMEM kernel: check it against the
     oracle biLSTM and against the cooperative-launch kernel on the same inputs, ragged lengths included."""

@@ -271,3 +271,35 @@ def test_sharded_batch_equals_single_batch_bitwise():
     full = run(0, 4)
     parts = torch.cat([run(*shard_range(4, r, 2)) for r in range(2)])
     assert torch.equal(full, parts)
+
+
+@pytest.mark.parametrize("model", ["ljspeech", "libritts"])
+def test_long_form_style_carry_over_matches_oracle(model):
+    """LFinference (LJSpeech notebook cell 29 / LibriTTS cell 42): the style of sentence k+1 is blended with the style
+    carried from sentence k (s_pred = t*s_prev + (1-t)*s_pred).  Two chained sentences, oracle vs kernels: the carried
+    style, the integer durations and F0 of the second sentence."""
+    from styletts2_b200.inference import Synthesizer
+    mcfg = cases.MODEL_CFGS[model]
+    m = gpu_model(model)
+    sds = oracle_sds(model)
+    syn = Synthesizer(m, mcfg, D)
+    s_prev_o, s_prev_g = None, None
+    for k, (N, seed) in enumerate([(11, 31), (8, 32)]):
+        case = dict(model=model, B=1, N=N, seed=seed)
+        tokens, lengths, bert_dur, noise, ref_s = cases.e2e_inputs(case)
+        rng = cases.ReplayRNG(seed)
+        steps = [rng.step_noise(i, (1, 1, 256)) for i in range(2)]
+        with torch.no_grad():
+            ref = O.synthesize(sds, mcfg, tokens, lengths, bert_dur, noise, diffusion_steps=3, ref_s=ref_s,
+                               rng=dict(step_noises=steps), s_prev=s_prev_o, t=0.7, skip_decoder=True)
+        out = syn.synthesize(tokens.to(D), lengths.to(D), bert_dur.to(D), noise.to(D), diffusion_steps=3,
+                             ref_s=None if ref_s is None else ref_s.to(D), rng=dict(step_noises=[s.to(D) for s in steps]),
+                             s_prev=s_prev_g, t=0.7, return_all=True)
+        ds = maxdiff(out["s_carry"], ref["s_carry"])
+        f0d = maxdiff(out["F0"], ref["F0"]) / max(1.0, float(ref["F0"].abs().max()))
+        record(f"long_form_{model}_sentence{k}", s_carry_maxabs=ds, F0_rel=f0d)
+        assert ds < 2e-5, ds
+        assert torch.equal(out["pred_dur"].cpu().float(), ref["pred_dur"])
+        assert f0d < 1e-4, f0d
+        assert torch.isfinite(out["wav"]).all()
+        s_prev_o, s_prev_g = ref["s_carry"], out["s_carry"]

@@ -30,7 +30,8 @@ def run(B, C, K, d, L, res, label):
     names = ["MMA ", "WPRD", "STAG", "EPI "]
     for it in range(6):
         row = []
-        for role in range(4):
+        for role in (0, 3):   # the kernel records the MMA issuer (waits: TMEM-empty, act-full, weights-full) and one epilogue warp
+                              # (waits: TMEM-full; cycles in residual+TMEM load, row stores, statistics); producer / stager slots are unused
             s_, e_ = int(t[role, it, 0]) - base, int(t[role, it, 1]) - base
             extra = [int(v) for v in t[role, it, 2:6]]
             row.append(f"{names[role]} [{s_:>7},{e_:>7}] w={extra}")
