@@ -5,7 +5,7 @@ is split contiguously across ranks with replicated weights and NO collective on 
 from __future__ import annotations
 
 import os
-from typing import Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import torch
 
@@ -15,6 +15,31 @@ def shard_range(batch: int, rank: int, world: int) -> Tuple[int, int]:
     base, rem = divmod(batch, world)
     start = rank * base + min(rank, rem)
     return start, start + base + (1 if rank < rem else 0)
+
+
+def plan_equal_length_batches(lengths: Sequence[int], world: int, max_batch: int) -> List[List[List[int]]]:
+    """Serving-side plan for a queue of utterances with DIFFERENT token counts (host part only): the
+    batched engine needs equal-length batches (Synthesizer.synthesize), so utterances are bucketed by token count, cut into
+    batches of at most `max_batch`, and the batches are dealt to ranks longest-processing-time first (cost ~ tokens x
+    utterances) so that every GPU finishes at about the same time.  Deterministic (ties by first utterance index).
+    Returns plan[rank] = list of batches, each a list of utterance indices."""
+    assert world >= 1 and max_batch >= 1
+    buckets: Dict[int, List[int]] = {}
+    for i, n in enumerate(lengths):
+        buckets.setdefault(int(n), []).append(i)
+    batches = []
+    for n in sorted(buckets):
+        idx = buckets[n]
+        for k in range(0, len(idx), max_batch):
+            batches.append((n * len(idx[k:k + max_batch]), idx[k:k + max_batch]))
+    batches.sort(key=lambda b: (-b[0], b[1][0]))
+    load = [0] * world
+    plan: List[List[List[int]]] = [[] for _ in range(world)]
+    for cost, idx in batches:
+        r = min(range(world), key=lambda q: (load[q], q))
+        plan[r].append(idx)
+        load[r] += cost
+    return plan
 
 
 def init_from_env(backend: str = "nccl"):

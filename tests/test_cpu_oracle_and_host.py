@@ -163,3 +163,19 @@ def test_oracle_long_form_carry_over_properties():
     with torch.no_grad():
         ms = O.synthesize(oracle_sds("libritts"), cases.MODEL_CFGS["libritts"], tokens, lengths, bert_dur, noise, ref_s=ref_s, **kw)
     assert torch.equal(ms["s_carry"], torch.cat([ms["ref"], ms["s"]], dim=-1))
+
+
+def test_equal_length_batch_plan_covers_every_utterance_once_and_balances():
+    from styletts2_b200.parallel import plan_equal_length_batches
+    g = torch.Generator().manual_seed(0)
+    lengths = torch.randint(20, 60, (200,), generator=g).tolist()
+    for world in (1, 2, 8):
+        plan = plan_equal_length_batches(lengths, world, max_batch=8)
+        seen = sorted(i for r in plan for b in r for i in b)
+        assert seen == list(range(200))
+        for r in plan:
+            for b in r:
+                assert 1 <= len(b) <= 8 and len({lengths[i] for i in b}) == 1      # equal token count inside a batch
+        loads = [sum(lengths[i] for b in r for i in b) for r in plan]
+        assert max(loads) - min(loads) <= 8 * 60                                        # LPT: within one batch of each other
+        assert plan == plan_equal_length_batches(lengths, world, max_batch=8)            # deterministic
