@@ -179,3 +179,32 @@ def test_equal_length_batch_plan_covers_every_utterance_once_and_balances():
         loads = [sum(lengths[i] for b in r for i in b) for r in plan]
         assert max(loads) - min(loads) <= 8 * 60                                        # LPT: within one batch of each other
         assert plan == plan_equal_length_batches(lengths, world, max_batch=8)            # deterministic
+
+
+def test_fp16_two_plane_split_recipe_is_fp32_accurate():
+    """CPU emulation of the GEMM precision recipe (csrc/linear_tc.cu): x = h + l*2^-11 with h = fp16(x),
+    l = fp16((x-h)*2^11); product = h*h' + (h*l' + l*h')*2^-11 (l*l' dropped).  Without the 2^11 pre-scaling the low
+    plane of small operands is an fp16 subnormal and the error is ~100x larger; with it the dot-product error stays
+    at the fp32 level for operands spread over six decades."""
+    g = torch.Generator().manual_seed(0)
+    K = 1024
+    a = (torch.randn(64, K, generator=g) * 10.0 ** (torch.rand(1, K, generator=g) * 6 - 4)).double()
+    w = (torch.randn(48, K, generator=g) * 10.0 ** (torch.rand(48, 1, generator=g) * 3 - 3)).double()
+
+    def split(x, scale):
+        h = x.float().half()
+        l = ((x.float() - h.float()) * scale).half()
+        return h.double(), l.double()
+
+    exact = a @ w.t()
+    bound = a.abs() @ w.abs().t()
+    errs = {}
+    for scale in (2048.0, 1.0):
+        ah, al = split(a, scale)
+        wh, wl = split(w, scale)
+        approx = ah @ wh.t() + (ah @ wl.t() + al @ wh.t()) / scale
+        errs[scale] = float(((approx - exact).abs() / bound).max())
+    fp32 = float((((a.float() @ w.float().t()).double() - exact).abs() / bound).max())
+    assert errs[2048.0] < 4e-7, errs            # ~2^-22 per product, random signs
+    assert errs[1.0] > 20 * errs[2048.0], errs  # unscaled low plane loses its bits to fp16 subnormals
+    assert errs[2048.0] < 10 * max(fp32, 6e-8)
