@@ -253,7 +253,13 @@ def main():
         np.savez_compressed(os.path.join(GOLD, cname + ".npz"), wav=wav_ref.numpy(),
                             har_patch_idx=pidx, har_patch_val=pval)
 
-    with open(os.path.join(GOLD, "PINNING.json"), "w") as f:
+    pin_path = os.path.join(GOLD, "PINNING.json")
+    if os.path.exists(pin_path):   # keep entries written by the other pinning scripts (make_golden_style.py)
+        old = json.load(open(pin_path))
+        for k, v in old.items():
+            if k not in pin:
+                pin[k] = v
+    with open(pin_path, "w") as f:
         json.dump(pin, f, indent=1)
     print("golden fixtures written to", GOLD)
 
