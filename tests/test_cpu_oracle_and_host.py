@@ -208,3 +208,21 @@ def test_fp16_two_plane_split_recipe_is_fp32_accurate():
     assert errs[2048.0] < 4e-7, errs            # ~2^-22 per product, random signs
     assert errs[1.0] > 20 * errs[2048.0], errs  # unscaled low plane loses its bits to fp16 subnormals
     assert errs[2048.0] < 10 * max(fp32, 6e-8)
+
+
+def test_pinning_records_are_within_the_stated_bars():
+    """The committed pinning records (oracle vs the UNMODIFIED reference, written by oracle/make_golden*.py and
+    oracle/pin_sweep.py in the build container) stay within the bars DESIGN.md states."""
+    import json
+    pin = json.load(open(os.path.join(GOLD, "PINNING.json")))
+    sweep = json.load(open(os.path.join(GOLD, "PINNING_SWEEP.json")))
+    records = list(pin["cases"].values()) + list(sweep["cases"].values())
+    assert len(records) >= 9
+    for rec in records:
+        d = rec["diffs"]
+        assert d.get("pred_dur_mismatch", 0) == 0
+        for k, v in d.items():
+            if k != "pred_dur_mismatch":
+                assert v <= 1e-5 * max(1.0, rec.get("scale", {}).get(k, 1.0)), (k, v)
+    st = pin["style_libri"]
+    assert st["log_mel_max_abs"] <= 1e-4 and st["ref_s_max_abs"] <= 1e-5
