@@ -23,6 +23,36 @@ SWEEP = {
 }
 
 
+def style_sweep():
+    """compute_style path (row f2): other clip lengths / batch sizes than the committed fixture."""
+    import torchaudio
+
+    import ref_import
+    import style_oracle as SO
+    from styletts2_b200.synthetic import keyed_state_dict, synthetic_wave
+    nets, _ = ref_import.build_reference(cases.REF_CONFIG_FILE["libritts"])
+    sds = {}
+    for k in ("style_encoder", "predictor_encoder"):
+        sds[k] = keyed_state_dict({n: tuple(v.shape) for n, v in nets[k].state_dict().items()}, k)
+        nets[k].load_state_dict(sds[k])
+        nets[k].eval()
+    to_mel = torchaudio.transforms.MelSpectrogram(n_mels=80, n_fft=2048, win_length=1200, hop_length=300)
+    res = {}
+    for name, (B, samples, seed) in {"b1_101f": (1, 30000, 21), "b3_152f": (3, 45300, 22), "b1_80f": (1, 23999, 23)}.items():
+        wave = synthetic_wave(B, samples, seed)
+        with torch.no_grad():
+            mel_ref = (torch.log(1e-5 + to_mel(wave)) + 4) / 4
+            ref = torch.cat([nets["style_encoder"](mel_ref.unsqueeze(1)), nets["predictor_encoder"](mel_ref.unsqueeze(1))], dim=1)
+            orc = SO.compute_style(sds, wave)
+            d_mel = float((SO.log_mel(wave) - mel_ref).abs().max())
+        d = float((orc - ref).abs().max())
+        print("style", name, "frames", mel_ref.shape[-1], "log-mel", d_mel, "ref_s", d, "scale", float(ref.abs().max()))
+        assert d_mel <= 1e-4 and d <= 1e-5
+        res[name] = dict(B=B, samples=samples, frames=int(mel_ref.shape[-1]), log_mel_max_abs=d_mel, ref_s_max_abs=d,
+                         ref_s_absmax=float(ref.abs().max()))
+    return res
+
+
 def main():
     torch.set_num_threads(8)
     models = load_models()   # also rewrites state_shapes_*.json with identical content
@@ -54,6 +84,7 @@ def main():
             if k != "pred_dur_mismatch":
                 assert v <= 1e-5 * max(1.0, float(ref[k].abs().max())), (cname, k, v)
         out["cases"][cname] = dict(case=case, diffs=diffs, scale=scale, T=int(ref["forced_dur"][0].sum()))
+    out["style"] = style_sweep()
     with open(os.path.join(GOLD, "PINNING_SWEEP.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("wrote PINNING_SWEEP.json")
