@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define ST2_ABI_VERSION 1
+#define ST2_ABI_VERSION 2
 
 /* activation codes (prologue / epilogue selectors) */
 #define ST2_ACT_NONE 0
@@ -91,23 +91,35 @@ int st2_conv1d(const st2_conv_args* a, void* stream);
 int st2_conv_stats_parts(int Lq);
 
 /* Tensor-core path of the same fused Conv1d (stride 1): tcgen05 implicit GEMM with TMEM accumulators,
- * bf16 hi/lo split operands (hi*hi + hi*lo + lo*hi, fp32 accumulate), weights streamed by 1-D TMA bulk
- * copies.  `wtc` is the st2_conv_tc_weight_layout buffer (st2_conv_tc_weight_bytes bytes) built from the
- * folded fp32 weight [Cout,Cin,K].  a->w is ignored; every other field means what it means for st2_conv1d,
+ * operands split into planes so that 16-bit / 8-bit tensor-core products reproduce the fp32 convolution (fp32
+ * accumulate), weights streamed by 1-D TMA bulk copies.  `mode` selects the precision recipe (csrc/conv_tc.cu):
+ *   ST2_TC_FAST      fp16 high planes + ONE e4m3 K=32 MMA carrying both correction terms: 2 MMA-times per product,
+ *                    error ~2^-16 per product (vocoder / decoder convolutions; waveform bar 1e-3);
+ *   ST2_TC_ACCURATE  two fp16 planes per operand, 3 MMAs, separate TMEM accumulator for the correction terms: error at
+ *                    the fp32-SIMT level (F0 / N predictor: F0 is integrated into a phase of 1e4..1e6 rad downstream);
+ *   ST2_TC_F16X3     the accurate planes in a single accumulator (A/B testing).
+ * `wtc` is the st2_conv_tc_weight_layout buffer (st2_conv_tc_weight_bytes bytes) built from the folded fp32 weight
+ * [Cout,Cin,K] FOR THE SAME mode.  a->w is ignored; every other field means what it means for st2_conv1d,
  * except that it writes TWO statistics partials per 256-column tile (stats_nparts >= offset + 2*ceil(Lq/256)).
+ * x must live in an allocation whose first byte is 16-byte aligned (cudaMalloc / the PyTorch caching allocator):
+ * rows are fetched as 16-byte copies of their aligned superset window.  Operand range: |z| < 1000 after the
+ * prologue, |w| < 16 (fp16 planes of 64 z and 4096 w); larger values give inf/NaN loudly.
  * max_ctas > 0 caps the persistent grid (testing).  Same call sites as st2_conv1d. */
+#define ST2_TC_FAST 0
+#define ST2_TC_ACCURATE 1
+#define ST2_TC_F16X3 2
 long long st2_conv_tc_weight_bytes(int Cout, int Cin, int K);
-int st2_conv_tc_weight_layout(const float* w, void* out, int Cout, int Cin, int K, void* stream);
+int st2_conv_tc_weight_layout(const float* w, void* out, int Cout, int Cin, int K, int mode, void* stream);
 int st2_conv_tc_supported(int Cin, int Cout, int K, int stride, int dil);
-int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int max_ctas, void* stream);
+int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int mode, int max_ctas, void* stream);
 /* Profiling aid: when set to a device buffer of 4*16*8 int64, CTA 0 of st2_conv1d_tc records per-role cycle
  * counters for its first 16 tiles (role 0 MMA, 1 weight producer, 2 stagers, 3 epilogue); NULL disables. */
 int st2_debug_set_trace(void* buf);
 /* Polyphase ConvTranspose1d on the same tensor-core kernel (one launch per phase); wtc from
  * st2_convT_tc_weight_layout (st2_convT_tc_weight_bytes bytes).  Arguments as st2_conv_transpose1d. */
 long long st2_convT_tc_weight_bytes(int Cin, int Cout, int K, int S);
-int st2_convT_tc_weight_layout(const float* w, void* out, int Cin, int Cout, int K, int S, int P, void* stream);
-int st2_conv_transpose1d_tc(const st2_conv_args* a, const void* wtc, int K, int S, int P, int reflect_left1, void* stream);
+int st2_convT_tc_weight_layout(const float* w, void* out, int Cin, int Cout, int K, int S, int P, int mode, void* stream);
+int st2_conv_transpose1d_tc(const st2_conv_args* a, const void* wtc, int mode, int K, int S, int P, int reflect_left1, void* stream);
 
 /* ConvTranspose1d (stride S, K taps, padding P; output length Lin*S) as S polyphase
  * stride-1 convolutions through the same fused kernel; `a` describes the x / y / prologue /
@@ -225,9 +237,12 @@ int st2_axpby(const float* x, float a, const float* y, float b, float* out, int 
 /* ------------------------------------------------------------------ text / duration glue
  * out[b,c,n] = (n < lengths[b]) ? table[tokens[b,n], c] : 0   (models.py:303-306) */
 int st2_embedding_cl(const long long* tokens, const float* table, const int* lengths, int B, int N, int C, float* out, void* stream);
-/* pred_dur[b,n] = max(1, rint(sum_j sigmoid(logits[b,n,j]))) (+last_plus on n==N-1)  -- integer boundary
- * (Inference_LJSpeech.ipynb#cell17).  dur_f (optional) receives the pre-rounding sums. */
-int st2_durations(const float* logits, int B, int N, int J, int last_plus, int* pred_dur, float* dur_f, void* stream);
+/* pred_dur[b,n] = max(1, rint(sum_j sigmoid(logits[b,n,j]))) (+last_plus on the last REAL token n==lengths[b]-1)
+ * -- integer boundary (Inference_LJSpeech.ipynb#cell17: `pred_dur[-1] += 5`; cell 29 / LibriTTS cell 16: no increment).
+ * lengths [B] int32 or NULL (= N): padded tokens n >= lengths[b] get duration 0 (they emit no frames, as when the
+ * reference runs the utterance alone).  dur_f (optional) receives the pre-rounding sums. */
+int st2_durations(const float* logits, int B, int N, int J, int last_plus, const int* lengths, int* pred_dur, float* dur_f,
+                  void* stream);
 /* frame -> token map from durations: tok[b,t] for t < T (T = row length), exclusive scan per utterance;
  * frames beyond sum(dur[b]) map to the last token.  total[b] = sum(dur[b]). */
 int st2_frame_tokens(const int* dur, int B, int N, int T, int shift_right, int* tok, int* total, void* stream);

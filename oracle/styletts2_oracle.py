@@ -515,7 +515,8 @@ def adpm2_sample(noise, sd: SD, num_steps: int, embedding, features=None, embedd
 # --------------------------------------------------------------------------- end to end glue
 def synthesize(sds: Dict[str, SD], model_cfg, tokens, input_lengths, bert_dur, noise, *,
                diffusion_steps=5, embedding_scale=1.0, ref_s=None, alpha=0.3, beta=0.7,
-               rng=None, forced_durations=None, sigma_data=0.2, s_prev=None, t=0.7, skip_decoder=False):
+               rng=None, forced_durations=None, sigma_data=0.2, s_prev=None, t=0.7, skip_decoder=False, last_plus=None,
+               front_only=False):
     """Batched (equal-length) version of the notebook `inference` glue
     (Demo/Inference_LJSpeech.ipynb#cell17 single-speaker; Demo/Inference_LibriTTS.ipynb#cell16
     multispeaker when ref_s is given).  `bert_dur` [B,N,768] is PL-BERT's output (an
@@ -523,6 +524,8 @@ def synthesize(sds: Dict[str, SD], model_cfg, tokens, input_lengths, bert_dur, n
     'rand_ini', 'sine_noise', 'har' (teacher-forced STFT features).  s_prev / t: the long-form style carry-over of
     `LFinference` (Demo/Inference_LJSpeech.ipynb#cell29, Demo/Inference_LibriTTS.ipynb#cell42): s_pred = t*s_prev +
     (1-t)*s_pred before the split; 's_carry' is what the notebook returns as the next s_prev.
+    last_plus: frames added to the last token's duration; None = the notebooks' `inference` convention (5 for the
+    single-speaker cell 17, 0 for LibriTTS cell 16); the LJSpeech LFinference (cell 29) has NO increment -> pass 0.
     Returns a dict of every stage boundary."""
     rng = rng or {}
     dec_cfg = model_cfg["decoder"]
@@ -545,7 +548,10 @@ def synthesize(sds: Dict[str, SD], model_cfg, tokens, input_lengths, bert_dur, n
     pred = sds["predictor"]
     d = duration_encoder(d_en, s, input_lengths, mask, sub(pred, "text_encoder"))
     logits = duration_logits(d, pred)
-    pred_dur = predict_durations(logits, 0 if multispeaker else 5)
+    pred_dur = predict_durations(logits, (0 if multispeaker else 5) if last_plus is None else last_plus)
+    if front_only:   # text side only (up to the integer boundary): any batch, totals need not agree
+        return dict(t_en=t_en, d_en=d_en, s_pred=s_pred, s=s, ref=ref, d=d, logits=logits, pred_dur=pred_dur, s_carry=s_carry,
+                    dur_f=torch.sigmoid(logits).sum(dim=-1))
     use_dur = pred_dur if forced_durations is None else forced_durations
     alns = [alignment_from_durations(use_dur[b]) for b in range(use_dur.shape[0])]
     T = alns[0].shape[1]

@@ -2,28 +2,42 @@
 //
 //   D[co (M=128), t (N=256)] = sum_{tap} sum_{ci} W_tap[co, ci] * z[ci, t + tap*dil - pad],   z = snake/lrelu(a*x+b)
 //
-// Precision recipe (decided with the CPU oracle, DESIGN.md "precision"): fp32 operands are split into
-// bf16 hi + bf16 lo and every product is evaluated as hi*hi + hi*lo + lo*hi on the 5th-gen tensor
-// cores with fp32 accumulation in TMEM (error ~2^-16 relative per product, 2.8e-5 max-abs on the
-// waveform vs 1.3e-3 for single-pass TF32 and 1.2e-2 for plain bf16).
+// Precision recipes (decided with the CPU oracle by emulation, DESIGN.md "precision"; tools/emulate_precision.py):
+// operands are pre-scaled by exact powers of two, w' = w * 2^12 and z' = z * 2^6 (the epilogue multiplies by 2^-18), so
+// that the fp16 "high" planes h = fp16(.) and the remainders l = (.) - h stay far away from fp16's subnormal range.
+//   ST2_TC_FAST  (vocoder / decoder, 2 MMA-times per product, double-buffered accumulator):
+//       D += h(w') h(z')                                   one kind::f16 MMA   (K = 16 channels)
+//          + [l(w')*2^4 | h(w')*2^-8] . [h(z')*2^-4 ; l(z')*2^8]   one kind::f8f6f4 MMA (e4m3, K = 32 = both corrections)
+//     the correction terms are 2^-11 of the leading one and e4m3 keeps 4 of their bits: ~15-16 operand bits in total,
+//     waveform error equal to the earlier bf16 hi/lo x3 recipe (emulated 3.9e-5 / 1.8e-4 vs 2.6e-5 / 1.1e-4 max-abs on the
+//     LJSpeech / LibriTTS decoder cases) at two thirds of its tensor-pipe time.  fp8 MMAs run at twice the fp16 rate, so
+//     the K=32 correction costs what one fp16 K=16 MMA costs.
+//   ST2_TC_ACCURATE (F0/N predictor: its F0 curve is integrated into a phase of 1e4..1e6 rad downstream):
+//       D0 += h(w') h(z');   D1 += h(w') l(z')*2^8 + l(w')*2^8 h(z')      three kind::f16 MMAs, TWO TMEM accumulators
+//     (the tensor core truncates when it adds into an accumulator: keeping the small terms out of the big running sum
+//     brings the error to the fp32-SIMT level, see linear_tc.cu); the epilogue folds D1 in with an exact 2^-8.
+//     Both accumulators take 2 x 256 TMEM columns, so this mode is not double buffered (small layers only).
+//   ST2_TC_F16X3: the accurate planes accumulated into ONE double-buffered accumulator (3 MMAs; kept for A/B tests).
 //
 // Mapping:
-//  * A operand = weights  [128 co x 16 ci] bf16, K-major, no-swizzle "interleave" layout (8-row x 16-byte core
-//    matrices, rows contiguous at 16 B pitch).  Pre-arranged in HBM so that one pipeline stage (tap, 32 ci,
-//    hi+lo) is ONE contiguous 16 KB block moved by a single 1-D TMA bulk copy (cp.async.bulk) that signals
+//  * A operand = weights  [128 co x 16 ci], K-major, no-swizzle "interleave" layout (8-row x 16-byte core
+//    matrices, rows contiguous at 16 B pitch).  Pre-arranged in HBM so that one pipeline stage (tap, 16 ci,
+//    both planes) is ONE contiguous 8 KB block moved by a single 1-D TMA bulk copy (cp.async.bulk) that signals
 //    an mbarrier.
-//  * B operand = activations [256 t x 16 ci] bf16, K-major, same interleave layout: for each group of 8
-//    input channels the frame window is a column of 16-byte rows, so a conv tap is just a descriptor start
-//    address shifted by tap*dil rows (16 B granularity) -- the window is staged ONCE per 32-channel block
-//    (AdaIN affine + Snake/LeakyReLU + hi/lo split fused into the staging) and re-used by all K taps.
-//  * D accumulators live in TMEM (2 x 256 columns, double buffered so the epilogue of tile i overlaps the
-//    MMAs of tile i+1); the epilogue reads them with tcgen05.ld, transposes 32x32 blocks through shared
-//    memory for coalesced row stores and fuses bias, residual, MRF accumulation and the InstanceNorm
+//  * B operand = activations [256 t x 16 ci], K-major, same interleave layout: for each K chunk the frame window is a
+//    column of 16-byte rows, so a conv tap is just a descriptor start address shifted by tap*dil rows (16 B
+//    granularity) -- the window is staged ONCE per 16-channel block (AdaIN affine + Snake/LeakyReLU + plane split
+//    fused into the staging) and re-used by all K taps.
+//  * Raw fp32 frame windows travel HBM -> shared memory as 16-byte cp.async copies of the ALIGNED superset window of
+//    every channel row (rows of odd length start at any 4-byte phase; the phase becomes a per-channel offset of the
+//    scalar shared-memory reads of the conversion), four 20 KB blocks in flight per SM.
+//  * D accumulators live in TMEM (2 x 256 columns); the epilogue reads them with tcgen05.ld, transposes 32x32 blocks
+//    through shared memory for coalesced row stores and fuses bias, residual, MRF accumulation and the InstanceNorm
 //    partial statistics (count, mean, M2) exactly like the SIMT kernel.
 //  * Warp roles: warp 0 = TMEM alloc + single-thread MMA issue, warp 1 = weight TMA producer,
-//    warps 2-11 = activation stagers, warps 12-19 = epilogue.
-//    Persistent CTAs (one per SM) loop over tiles.
-#include <cuda_bf16.h>
+//    warps 2-11 = activation stagers, warps 12-19 = epilogue.  Persistent CTAs (one per SM) loop over tiles.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -33,23 +47,33 @@ extern long long g_launches;
 
 namespace tc {
 
+constexpr int MODE_FAST = ST2_TC_FAST, MODE_ACC = ST2_TC_ACCURATE, MODE_X3 = ST2_TC_F16X3;
+
 constexpr int TN = 256;
 constexpr int TM = 128;
-constexpr int CB = 16;                          // input channels per pipeline block (2 K-chunks of 8 = one UMMA K step)
-constexpr int KCB = CB / 8;                     // K-chunks per block
+constexpr int CB = 16;                          // input channels per pipeline block (one UMMA K step of the fp16 planes)
+constexpr int KCB = CB / 8;                     // 16-byte K chunks per plane and block
 constexpr int W_STAGES = 6;
-constexpr int W_STAGE_BYTES = 2 * KCB * TM * 16;  // (hi|lo) x 2 k-chunks x 128 co x 16 B = 8 KB
+constexpr int W_PLANE_BYTES = KCB * TM * 16;    // 4 KB
+constexpr int W_STAGE_BYTES = 2 * W_PLANE_BYTES;  // plane 0 (fp16 high) | plane 1 (fp8 corrections or fp16 low) = 8 KB
 constexpr int RW_MAX = 312;                     // TN + (K-1)*dil rounded up to 8, max
-constexpr int RWP_MAX = RW_MAX + 2;             // chunk pitch in rows: == 2 (mod 8) -> conflict-free 128-bit staging stores
-constexpr int ACT_HALF_BYTES = KCB * RWP_MAX * 16;  // one of hi / lo for one 16-channel block
-constexpr int ACT_BUF_BYTES = 2 * ACT_HALF_BYTES;
+constexpr int RWP_MAX = RW_MAX + 2;             // chunk pitch in rows of the staged planes
+constexpr int ACT_PLANE_BYTES = KCB * RWP_MAX * 16;  // one plane of one 16-channel block
+constexpr int ACT_BUF_BYTES = 2 * ACT_PLANE_BYTES;
 constexpr int RAW_STAGES = 4;                   // cp.async ring of raw fp32 frame windows: 3 blocks (60 KB) in flight per SM
-constexpr int RAW_BYTES = CB * RWP_MAX * 4;     // 20 KB
+constexpr int RAW_PITCH = 320;                  // floats per channel row of a raw block: 80 16-byte chunks >= RW_MAX + 3
+constexpr int RAW_CHUNKS = RAW_PITCH / 4;
+constexpr int RAW_BYTES = CB * RAW_PITCH * 4;   // 20 KB
 constexpr int CIN_PAD_MAX = 1120;
 constexpr int NUM_STAGERS = 320;                // 10 warps
 constexpr int NUM_EPI = 256;                    // 8 warps: two per TMEM lane quarter (each takes half of the columns)
 constexpr int THREADS = 64 + NUM_STAGERS + NUM_EPI;  // 640 = 20 warps (register allocation granularity: 4 warps)
 constexpr int TPITCH = 36;                      // epilogue transpose row pitch (floats), 16-byte aligned rows
+
+// power-of-two operand scaling (exact): w' = w * 2^12, z' = z * 2^6; accumulators hold 2^18 x the convolution
+constexpr float W_SCALE = 4096.0f, X_SCALE = 64.0f, D_UNSCALE = 1.0f / (4096.0f * 64.0f);
+constexpr float ACC_LO_SCALE = 256.0f, ACC_LO_UNSCALE = 1.0f / 256.0f;            // ST2_TC_ACCURATE low planes
+constexpr float F8_WLO = 16.0f, F8_WHI = 1.0f / 256.0f, F8_XHI = 1.0f / 16.0f, F8_XLO = 256.0f;  // e4m3 correction operands
 
 constexpr int SM_W = 0;
 constexpr int SM_ACT = SM_W + W_STAGES * W_STAGE_BYTES;
@@ -58,6 +82,7 @@ constexpr int SM_COEF = SM_RAW + RAW_STAGES * RAW_BYTES;
 constexpr int SM_EPI = SM_COEF + 4 * CIN_PAD_MAX * 4;
 constexpr int SM_BAR = SM_EPI + 8 * (32 * TPITCH + 32) * 4;
 constexpr int SM_TOTAL = SM_BAR + 256;
+static_assert(SM_TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 
 // barrier slots (8 B each) inside SM_BAR
 constexpr int B_WFULL = 0, B_WEMPTY = 6, B_AFULL = 12, B_AEMPTY = 14, B_TFULL = 16, B_TEMPTY = 18, B_COUNT = 20;
@@ -78,17 +103,25 @@ __device__ __forceinline__ long long mbar_wait_timed(uint32_t bar, uint32_t pari
   return clock64() - t0;
 }
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256.
+// Instruction descriptor: D = f32, A and B format code 0 (= F16 for kind::f16, = E4M3 for kind::f8f6f4), both K-major,
+// M = 128, N = 256.  The same bits serve both kinds.
 __device__ __forceinline__ uint32_t make_idesc() {
   uint32_t d = 0;
-  d |= 1u << 4;                 // c_format = F32
-  d |= 1u << 7;                 // a_format = BF16
-  d |= 1u << 10;                // b_format = BF16
+  d |= 1u << 4;                    // c_format = F32
   d |= (uint32_t)(TN >> 3) << 17;  // n_dim
   d |= (uint32_t)(TM >> 4) << 24;  // m_dim
   return d;
 }
-
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // Output channels of a 128-row tile are spread over the four TMEM lane quarters (an epilogue warp can only read the
 // quarter warp_id % 4): quarter q holds channels co0 + q*rq .. + rq-1 with rq = ceil(min(Cout - co0, 128) / 4).  For full
@@ -111,38 +144,63 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int n_tq, int n_cob) {
   return c;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
 // ---------------------------------------------------------------------------------------------
-// Stager inner work: AdaIN affine + activation + bf16 hi/lo split + two 128-bit stores for one frame row
-// (8 channels of one K-chunk).  Templated on the activation so the per-element code has no branches.
-template <int ACT>
+// Stager inner work for one frame row (8 channels of one K chunk): AdaIN affine + activation (coefficients carry the
+// 2^6 operand scale) + plane split + shared-memory stores.  Templated on activation and recipe: no branches per element.
+//   p0 row: 8 fp16 (16 B) at chunk kc.   p1 row: MODE_FAST -> 8 + 8 e4m3 bytes (the kc-th half of the two 16-byte rows
+//   [h(z')/16 for 16 channels] and [l(z')*256 for 16 channels]);  otherwise 8 fp16 low-plane values (16 B) at chunk kc.
+template <int ACT, int MODE>
 __device__ __forceinline__ void stage_row(const float (&x)[8], const float (&pa)[8], const float (&pb)[8], const float (&al)[8],
-                                          const float (&ia)[8], float slope, bool inb, uint8_t* hi_dst, uint8_t* lo_dst) {
+                                          const float (&ia)[8], float slope, bool inb, uint8_t* p0, uint8_t* p1, int kc, int r,
+                                          int RWP) {
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float z = fmaf(x[j], pa[j], pb[j]);
+    float z = fmaf(x[j], pa[j], pb[j]);          // = 64 * (a*x + b)
     if (ACT == ST2_ACT_SNAKE) {
-      const float sn = __sinf(al[j] * z);
-      z = fmaf(ia[j], sn * sn, z);
+      const float sn = __sinf(al[j] * z);        // al = alpha / 64
+      z = fmaf(ia[j], sn * sn, z);               // ia = 64 / alpha
     } else if (ACT == ST2_ACT_LRELU) {
       z = z > 0.f ? z : z * slope;
     }
     v[j] = inb ? z : 0.f;  // zero padding applies AFTER the activation
   }
-  uint32_t hp[4], lp[4];
+  uint32_t hp[4];
+  float lo[8];
+  __half2 h2[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    hp[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
-    const float h0 = __uint_as_float(hp[q] << 16), h1 = __uint_as_float(hp[q] & 0xFFFF0000u);
-    lp[q] = pack_bf16(v[2 * q] - h0, v[2 * q + 1] - h1);
+    h2[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+    hp[q] = h2_bits(h2[q]);
+    const float2 hf = __half22float2(h2[q]);
+    lo[2 * q] = v[2 * q] - hf.x;
+    lo[2 * q + 1] = v[2 * q + 1] - hf.y;
   }
-  *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-  *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+  *reinterpret_cast<uint4*>(p0 + (size_t)(kc * RWP + r) * 16) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+  if (MODE == MODE_FAST) {
+    uint32_t h8[2], l8[2];
+    const __half2 sc = __floats2half2_rn(F8_XHI, F8_XHI);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const __half2 a0 = __hmul2(h2[2 * q], sc), a1 = __hmul2(h2[2 * q + 1], sc);
+      const uint32_t e0 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&a0), __NV_SATFINITE, __NV_E4M3);
+      const uint32_t e1 = __nv_cvt_halfraw2_to_fp8x2(*reinterpret_cast<const __half2_raw*>(&a1), __NV_SATFINITE, __NV_E4M3);
+      h8[q] = e0 | (e1 << 16);
+      const uint32_t f0 = __nv_cvt_float2_to_fp8x2(make_float2(lo[4 * q] * F8_XLO, lo[4 * q + 1] * F8_XLO), __NV_SATFINITE, __NV_E4M3);
+      const uint32_t f1 = __nv_cvt_float2_to_fp8x2(make_float2(lo[4 * q + 2] * F8_XLO, lo[4 * q + 3] * F8_XLO), __NV_SATFINITE, __NV_E4M3);
+      l8[q] = f0 | (f1 << 16);
+    }
+    *reinterpret_cast<uint2*>(p1 + (size_t)r * 16 + kc * 8) = make_uint2(h8[0], h8[1]);
+    *reinterpret_cast<uint2*>(p1 + (size_t)(RWP + r) * 16 + kc * 8) = make_uint2(l8[0], l8[1]);
+  } else {
+    const float ls = (MODE == MODE_ACC) ? ACC_LO_SCALE : 1.0f;
+    uint32_t lp[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) lp[q] = h2_bits(__floats2half2_rn(lo[2 * q] * ls, lo[2 * q + 1] * ls));
+    *reinterpret_cast<uint4*>(p1 + (size_t)(kc * RWP + r) * 16) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+  }
 }
 
 // Epilogue row loop for one 32x32 accumulator block already transposed into T: row r of the block is output
@@ -175,10 +233,12 @@ __device__ __forceinline__ void epi_rows(float* T, const float* bsm, float* yp, 
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int ncb, const int RW, const int ntiles,
                  const int n_tq, const int n_cob) {
   // RW = window rows (TN + (K-1)*dil, rounded up to 8); RWP = chunk pitch in rows
+  constexpr int NBUF = (MODE == MODE_ACC) ? 1 : 2;   // TMEM accumulator sets (ACCURATE needs both halves for one tile)
   const int RWP = RW + 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -216,30 +276,35 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       auto wait_pumping = [&](uint32_t bar, uint32_t parity) -> long long { return mbar_wait_timed(bar, parity); };
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
+        const int buf = it % NBUF;
         const long long tt0 = clock64();
-        long long w_te = wait_pumping(BAR(B_TEMPTY + buf), ((it >> 1) & 1) ^ 1), w_af = 0, w_wf = 0;
+        long long w_te = wait_pumping(BAR(B_TEMPTY + buf), ((it / NBUF) & 1) ^ 1), w_af = 0, w_wf = 0;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)buf * TN;
+        const uint32_t d0 = tmem_base + (uint32_t)buf * TN;
+        const uint32_t d1 = (MODE == MODE_ACC) ? tmem_base + TN : d0;
         uint32_t first = 1;
         for (int cb = 0; cb < ncb; ++cb) {
           w_af += wait_pumping(BAR(B_AFULL + as), aph);
           tc_fence_after();
-          const uint32_t act_hi = sbase + SM_ACT + as * ACT_BUF_BYTES;
-          const uint32_t act_lo = act_hi + ACT_HALF_BYTES;
+          const uint32_t act0 = sbase + SM_ACT + as * ACT_BUF_BYTES;
+          const uint32_t act1 = act0 + ACT_PLANE_BYTES;
           for (int tap = 0; tap < K; ++tap) {
             w_wf += wait_pumping(BAR(B_WFULL + ws), wph);
             tc_fence_after();
-            const uint32_t w_hi = sbase + SM_W + ws * W_STAGE_BYTES;
-            const uint32_t w_lo = w_hi + W_STAGE_BYTES / 2;
+            const uint32_t w0 = sbase + SM_W + ws * W_STAGE_BYTES;
+            const uint32_t w1 = w0 + W_PLANE_BYTES;
             const uint32_t row_off = (uint32_t)(tap * a.dil) * 16;
             {
-              const uint64_t da_hi = make_desc(w_hi, lbo_a, 128), da_lo = make_desc(w_lo, lbo_a, 128);
-              const uint64_t db_hi = make_desc(act_hi + row_off, lbo_b, 128), db_lo = make_desc(act_lo + row_off, lbo_b, 128);
-              tc_mma(d_tmem, da_hi, db_hi, idesc, first ? 0u : 1u);
+              const uint64_t da0 = make_desc(w0, lbo_a, 128), da1 = make_desc(w1, lbo_a, 128);
+              const uint64_t db0 = make_desc(act0 + row_off, lbo_b, 128), db1 = make_desc(act1 + row_off, lbo_b, 128);
+              tc_mma(d0, da0, db0, idesc, first ? 0u : 1u);
+              if (MODE == MODE_FAST) {
+                tc_mma_f8(d0, da1, db1, idesc, 1u);              // both corrections in one e4m3 K=32 MMA
+              } else {
+                tc_mma(d1, da0, db1, idesc, (MODE == MODE_ACC && first) ? 0u : 1u);
+                tc_mma(d1, da1, db0, idesc, 1u);
+              }
               first = 0;
-              tc_mma(d_tmem, da_hi, db_lo, idesc, 1u);
-              tc_mma(d_tmem, da_lo, db_hi, idesc, 1u);
             }
             tc_commit(BAR(B_WEMPTY + ws));
             if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
@@ -271,9 +336,12 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     }
   } else if (warp < 2 + NUM_STAGERS / 32) {
     // ================================================================ activation stagers
-    // Raw fp32 frame windows travel HBM -> shared memory with cp.async (no registers held while in flight): a ring
-    // of RAW_STAGES 16-channel blocks keeps ~60 KB per SM outstanding, which is what it takes to cover HBM latency.
-    // Conversion (AdaIN affine + Snake/LeakyReLU + bf16 hi/lo split) reads the landed block from shared memory.
+    // Raw fp32 frame windows travel HBM -> shared memory with 16-byte cp.async copies (no registers held while in
+    // flight): a ring of RAW_STAGES 16-channel blocks keeps ~60 KB per SM outstanding, which is what it takes to cover
+    // HBM latency.  Rows of the activation tensor start at any 4-byte phase (odd row lengths), so each channel row
+    // copies the 16-byte ALIGNED superset of its window; the phase (0..3 floats) is re-derived by the conversion.
+    // Chunks outside the tensor are zero-filled (src-size 0), the chunk that crosses the end of the tensor is
+    // trimmed; nothing before the 16-byte aligned start of the tensor's allocation is ever touched.
     const int st = tid - 64;  // 0..319
     const int Lin_ = a.Lin, pre_act_ = a.pre_act, Cin_ = a.Cin;
     const float slope_ = a.pre_slope;
@@ -281,30 +349,40 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     const int cin_pad = ncb * CB;
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_blocks = my_tiles * ncb;
-    // issue mapping: thread -> one channel of the block (st / 20) and every 20th frame row: pointer increments only
-    const int ich = st / 20, ir0 = st - ich * 20;
-    int i_tile = -1, i_b = 0, i_g0 = 0;  // producer-side tile state (runs 3 blocks ahead of the conversion)
-    const float* i_xb = a.x;
+    const unsigned long long xaddr4 = (unsigned long long)(uintptr_t)a.x >> 2;
+    const long long tensor_end = (long long)(a.B - 1) * a.x_bstride + (long long)Cin_ * Lin_;  // floats from a.x
+    const float* x_al = reinterpret_cast<const float*>((uintptr_t)a.x & ~(uintptr_t)15);
+    // issue mapping: thread -> one channel of the block (st / 20) and every 20th 16-byte chunk of its row
+    const int ich = st / 20, iq0 = st - ich * 20;
+    int i_tile = -1, i_g0 = 0;  // producer-side tile state (runs 3 blocks ahead of the conversion)
+    long long i_boff = 0;
     auto issue = [&](int g) {
       if (g < total_blocks) {
         const int tl = g / ncb, cb = g - tl * ncb;
         if (tl != i_tile) {
           i_tile = tl;
           const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
-          i_b = tc_.b;
-          i_xb = a.x + (long long)tc_.b * a.x_bstride;
+          i_boff = (long long)tc_.b * a.x_bstride;
           i_g0 = tc_.tq * TN - a.pad;
         }
         const int c = cb * CB + ich;
-        const int rlo = (c < Cin_) ? max(0, -i_g0) : RW;   // rows [rlo, rhi) are inside the tensor; the rest zero-fill
-        const int rhi = min(RW, Lin_ - i_g0);
-        const float* src = i_xb + (long long)min(c, Cin_ - 1) * Lin_ + (i_g0 + ir0);
-        uint32_t dst = sbase + SM_RAW + (g % RAW_STAGES) * RAW_BYTES + (uint32_t)(ich * RWP + ir0) * 4;
-        for (int r = ir0; r < RW; r += 20) {
-          const bool ok = (r >= rlo) && (r < rhi);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(ok ? src : a.x), "r"(ok ? 4 : 0) : "memory");
-          src += 20;
-          dst += 80;
+        const long long e0 = i_boff + (long long)min(c, Cin_ - 1) * Lin_ + i_g0;   // first window element, floats from a.x
+        const int shift = (int)((xaddr4 + (unsigned long long)e0) & 3ull);
+        const int rlo = max(0, -i_g0), rhi = min(RW, Lin_ - i_g0);              // rows [rlo, rhi) are inside the tensor
+        int qlo = 0, qhi = 0;
+        if (c < Cin_ && rhi > rlo) { qlo = (rlo + shift) >> 2; qhi = (rhi + shift + 3) >> 2; }
+        const long long w0 = e0 - shift;                                          // aligned window start, floats from a.x
+        const float* src0 = a.x + w0;
+        const long long end_rel = tensor_end - w0;
+        uint32_t dst = sbase + SM_RAW + (g % RAW_STAGES) * RAW_BYTES + (uint32_t)(ich * RAW_PITCH + iq0 * 4) * 4;
+#pragma unroll
+        for (int i = 0; i < RAW_CHUNKS / 20; ++i) {
+          const int q = iq0 + 20 * i;
+          const bool ok = (q >= qlo) && (q < qhi);
+          const long long rem = end_rel - 4ll * q;
+          const int nbytes = ok ? (rem >= 4 ? 16 : (int)rem * 4) : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src0 + 4 * q : x_al), "r"(nbytes) : "memory");
+          dst += 20 * 16;
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -314,14 +392,20 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     issue(2);
     int as = 0, aph = 0;
     int last_b = -1, c_tile = -1, c_b = 0, c_g0 = 0;
-    const int kc = st & 1, rg = st >> 1;  // conversion mapping: 2 K-chunks x 160 row groups
+    long long c_boff = 0;
+    // conversion mapping: warp parity -> K chunk, (warp / 2, lane) -> 160 rows per pass: every shared-memory access of
+    // a warp touches consecutive words / consecutive 16-byte rows
+    const int sw = warp - 2;
+    const int kc = sw & 1, rg = (sw >> 1) * 32 + lane;
     constexpr int NRC = (RW_MAX + 159) / 160;
+    const float xs_ = X_SCALE;
     for (int g = 0; g < total_blocks; ++g) {
       const int tl = g / ncb, cb = g - tl * ncb;
       if (tl != c_tile) {
         c_tile = tl;
         const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
         c_b = tc_.b;
+        c_boff = (long long)tc_.b * a.x_bstride;
         c_g0 = tc_.tq * TN - a.pad;
       }
       asm volatile("cp.async.wait_group 2;" ::: "memory");
@@ -335,22 +419,27 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
             if (a.pre_a) { pa = a.pre_a[c_b * Cin_ + c]; pb = a.pre_b[c_b * Cin_ + c]; }
             if (pre_act_ == ST2_ACT_SNAKE) al = a.pre_alpha[c];
           }
-          coef[c] = pa; coef[CIN_PAD_MAX + c] = pb; coef[2 * CIN_PAD_MAX + c] = al; coef[3 * CIN_PAD_MAX + c] = 1.0f / al;
+          // the 2^6 operand scale is folded into the coefficients: z' = 64 z = (64a) x + 64b; snake(z) * 64 =
+          // z' + (64/alpha) sin^2((alpha/64) z'); LeakyReLU is positively homogeneous
+          coef[c] = pa * xs_; coef[CIN_PAD_MAX + c] = pb * xs_; coef[2 * CIN_PAD_MAX + c] = al / xs_; coef[3 * CIN_PAD_MAX + c] = xs_ / al;
         }
         asm volatile("bar.sync 2, %0;" ::"n"(NUM_STAGERS));
         last_b = c_b;
       }
       const int c0 = cb * CB + kc * 8;
       float pa[8], pb[8], al[8], ia[8];
+      int sh[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         pa[j] = coef[c0 + j]; pb[j] = coef[CIN_PAD_MAX + c0 + j]; al[j] = coef[2 * CIN_PAD_MAX + c0 + j];
         ia[j] = coef[3 * CIN_PAD_MAX + c0 + j];
+        const long long e0 = c_boff + (long long)min(c0 + j, Cin_ - 1) * Lin_ + c_g0;
+        sh[j] = (int)((xaddr4 + (unsigned long long)e0) & 3ull) + j * RAW_PITCH;
       }
-      const float* raw = reinterpret_cast<const float*>(smem + SM_RAW + (g % RAW_STAGES) * RAW_BYTES) + (kc * 8) * RWP;
+      const float* raw = reinterpret_cast<const float*>(smem + SM_RAW + (g % RAW_STAGES) * RAW_BYTES) + (kc * 8) * RAW_PITCH;
       mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
-      uint8_t* hi = smem + SM_ACT + as * ACT_BUF_BYTES;
-      uint8_t* lo = hi + ACT_HALF_BYTES;
+      uint8_t* p0 = smem + SM_ACT + as * ACT_BUF_BYTES;
+      uint8_t* p1 = p0 + ACT_PLANE_BYTES;
 #pragma unroll
       for (int i = 0; i < NRC; ++i) {
         const int r = rg + 160 * i;
@@ -359,12 +448,10 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           const bool inb = (gt >= 0) && (gt < Lin_);
           float xv[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) xv[j] = raw[j * RWP + r];
-          uint8_t* hd = hi + (size_t)(kc * RWP + r) * 16;
-          uint8_t* ld = lo + (size_t)(kc * RWP + r) * 16;
-          if (pre_act_ == ST2_ACT_SNAKE) stage_row<ST2_ACT_SNAKE>(xv, pa, pb, al, ia, slope_, inb, hd, ld);
-          else if (pre_act_ == ST2_ACT_LRELU) stage_row<ST2_ACT_LRELU>(xv, pa, pb, al, ia, slope_, inb, hd, ld);
-          else stage_row<ST2_ACT_NONE>(xv, pa, pb, al, ia, slope_, inb, hd, ld);
+          for (int j = 0; j < 8; ++j) xv[j] = raw[sh[j] + r];
+          if (pre_act_ == ST2_ACT_SNAKE) stage_row<ST2_ACT_SNAKE, MODE>(xv, pa, pb, al, ia, slope_, inb, p0, p1, kc, r, RWP);
+          else if (pre_act_ == ST2_ACT_LRELU) stage_row<ST2_ACT_LRELU, MODE>(xv, pa, pb, al, ia, slope_, inb, p0, p1, kc, r, RWP);
+          else stage_row<ST2_ACT_NONE, MODE>(xv, pa, pb, al, ia, slope_, inb, p0, p1, kc, r, RWP);
         }
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -386,7 +473,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
-      const int buf = it & 1;
+      const int buf = it % NBUF;
       const int rq = rows_per_quarter(Cout_, tc_.cob);
       const int co_base = tc_.cob * TM + ew * rq;
       const int t0 = tc_.tq * TN;
@@ -394,7 +481,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       const int rmax = min(rq, Cout_ - co_base);  // warp-uniform (may be <= 0 for padded channel blocks)
       bsm[lane] = (a.bias && lane < rmax) ? a.bias[co_base + lane] : 0.f;
       const long long ett0 = clock64();
-      const long long w_tf = mbar_wait_timed(BAR(B_TFULL + buf), (it >> 1) & 1);
+      const long long w_tf = mbar_wait_timed(BAR(B_TFULL + buf), (it / NBUF) & 1);
       tc_fence_after();
       float* yb = a.y + (long long)tc_.b * a.y_bstride + (long long)co_base * y_len_;
       const float* rb = a.res ? a.res + (long long)tc_.b * a.res_bstride + (long long)co_base * res_len_ : nullptr;
@@ -411,7 +498,19 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
 #pragma unroll
           for (int r = 0; r < 32; ++r) rv[r] = (rb && okc && r < rmax) ? __ldg(rp0 + (long long)r * res_len_) : 0.f;
         }
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + c0), v);
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + c0);
+        tmem_ld32(taddr, v);
+        if (MODE == MODE_ACC) {
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            float vl[16];
+            tmem_ld16(taddr + TN + 16 * hq, vl);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[16 * hq + j] = fmaf(vl[j], ACC_LO_UNSCALE, v[16 * hq + j]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= D_UNSCALE;
         const long long q1 = clock64();
         tr_ld += q1 - q0;
         if (c0 >= ncols || rmax <= 0) continue;
@@ -427,6 +526,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           float* yp = yb + oidx;
           const float* rp = rb ? rb + ridx : nullptr;
           const long long ys = y_len_, rs = res_len_;
+          (void)rp; (void)rs;
           if (out_act_ == ST2_ACT_NONE) {
 #define EPI(RES_, ACC_, ST_) epi_rows<RES_, ACC_, ST_>(T, bsm, yp, rv, ys, rmax, tv, lane, out_div_, acc_div_)
             if (has_stats) {
@@ -524,69 +624,108 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
   }
 }
 
-// fp32 [Cout,Cin,K] -> bf16 hi/lo stage blocks [K][n_cob][ncb][2][4][128][8]
-__global__ void conv_tc_weight_layout_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int K,
-                                             int n_cob, int ncb) {
-  const long long total = (long long)K * n_cob * ncb * 2 * KCB * TM * 8;
+// One element of a weight stage block [plane 2][chunk 2][128 rows][16 B]: byte index -> value.
+//   plane 0: fp16 high plane of w' = w * 2^12, chunk = channels 8*kc .. 8*kc+7 (2 bytes each).
+//   plane 1, ST2_TC_FAST: e4m3 bytes; chunk 0 = l(w') * 2^4 for the block's 16 channels, chunk 1 = h(w') * 2^-8.
+//   plane 1, otherwise:   fp16 low plane l(w') (* 2^8 for ST2_TC_ACCURATE).
+__device__ __forceinline__ void weight_stage_store(uint8_t* blk, int byte_in_stage, int mode, const float* wrow16 /* 16 channel values of this row */) {
+  const int plane = byte_in_stage / W_PLANE_BYTES;
+  const int r = byte_in_stage % W_PLANE_BYTES;
+  const int chunk = r / (TM * 16), within = r % 16;
+  if (plane == 0 || mode != MODE_FAST) {
+    if (within & 1) return;       // handled by the even byte
+    const float wv = wrow16[chunk * 8 + within / 2] * W_SCALE;
+    const __half h = __float2half_rn(wv);
+    __half o = h;
+    if (plane == 1) o = __float2half_rn((wv - __half2float(h)) * (mode == MODE_ACC ? ACC_LO_SCALE : 1.0f));
+    *reinterpret_cast<__half*>(blk + byte_in_stage) = o;
+  } else {
+    const float wv = wrow16[within] * W_SCALE;
+    const float hf = __half2float(__float2half_rn(wv));
+    const float val = (chunk == 0) ? (wv - hf) * F8_WLO : hf * F8_WHI;
+    blk[byte_in_stage] = (uint8_t)__nv_cvt_float_to_fp8(val, __NV_SATFINITE, __NV_E4M3);
+  }
+}
+
+// fp32 [Cout,Cin,K] -> stage blocks [K][n_cob][ncb] x 8 KB
+__global__ void conv_tc_weight_layout_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int Cout, int Cin, int K,
+                                             int n_cob, int ncb, int mode) {
+  // one thread per (stage, plane, chunk, row): writes the 16 bytes of that row
+  const long long total = (long long)K * n_cob * ncb * 2 * KCB * TM;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
-    const int j = (int)(r % 8); r /= 8;
     const int col = (int)(r % TM); r /= TM;
-    const int kc = (int)(r % KCB); r /= KCB;
-    const int hl = (int)(r % 2); r /= 2;
+    const int chunk = (int)(r % KCB); r /= KCB;
+    const int plane = (int)(r % 2); r /= 2;
     const int cb = (int)(r % ncb); r /= ncb;
     const int cob = (int)(r % n_cob); r /= n_cob;
     const int tap = (int)r;
     const int rq = rows_per_quarter(Cout, cob);
     const int qq = col >> 5, rr = col & 31;
-    const int co = cob * TM + qq * rq + rr, ci = cb * CB + kc * 8 + j;
-    float v = 0.f;
-    if (rr < rq && co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * K + tap];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    out[i] = hl == 0 ? h : __float2bfloat16_rn(v - __bfloat162float(h));
+    const int co = cob * TM + qq * rq + rr;
+    float wr[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int ci = cb * CB + j;
+      wr[j] = (rr < rq && co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * K + tap] : 0.f;
+    }
+    uint8_t* blk = out + ((long long)(tap * n_cob + cob) * ncb + cb) * W_STAGE_BYTES;
+    const int base = plane * W_PLANE_BYTES + (chunk * TM + col) * 16;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) weight_stage_store(blk, base + b, mode, wr);
   }
 }
 
 // ConvTranspose1d weight [Cin,Cout,K] -> S per-phase tensor-core blocks (phase r = J-tap stride-1 conv, see conv.cu)
-__global__ void convT_tc_weight_layout_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Cout, int K,
-                                              int S, int P, int J, int n_cob, int ncb) {
-  const long long per_phase = (long long)J * n_cob * ncb * 2 * KCB * TM * 8;
+__global__ void convT_tc_weight_layout_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int Cin, int Cout, int K,
+                                              int S, int P, int J, int n_cob, int ncb, int mode) {
+  const long long per_phase = (long long)J * n_cob * ncb * 2 * KCB * TM;
   const long long total = per_phase * S;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ph = (int)(i / per_phase);
     long long r = i % per_phase;
-    const int j = (int)(r % 8); r /= 8;
     const int col = (int)(r % TM); r /= TM;
-    const int kc = (int)(r % KCB); r /= KCB;
-    const int hl = (int)(r % 2); r /= 2;
+    const int chunk = (int)(r % KCB); r /= KCB;
+    const int plane = (int)(r % 2); r /= 2;
     const int cb = (int)(r % ncb); r /= ncb;
     const int cob = (int)(r % n_cob); r /= n_cob;
     const int kp = (int)r;  // tap of the phase conv
     const int rq = rows_per_quarter(Cout, cob);
     const int qq = col >> 5, rr = col & 31;
-    const int co = cob * TM + qq * rq + rr, ci = cb * CB + kc * 8 + j;
+    const int co = cob * TM + qq * rq + rr;
     const int kk = (J - 1 - kp) * S + ((ph + P) % S);
-    float v = 0.f;
-    if (rr < rq && co < Cout && ci < Cin && kk < K) v = w[((long long)ci * Cout + co) * K + kk];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    out[i] = hl == 0 ? h : __float2bfloat16_rn(v - __bfloat162float(h));
+    float wr[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int ci = cb * CB + j;
+      wr[j] = (rr < rq && co < Cout && ci < Cin && kk < K) ? w[((long long)ci * Cout + co) * K + kk] : 0.f;
+    }
+    uint8_t* blk = out + ((long long)ph * J * n_cob * ncb + (long long)(kp * n_cob + cob) * ncb + cb) * W_STAGE_BYTES;
+    const int base = plane * W_PLANE_BYTES + (chunk * TM + col) * 16;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) weight_stage_store(blk, base + b, mode, wr);
   }
 }
 
-static int launch_tc(const st2_conv_args& a, const void* wtc, int max_ctas, cudaStream_t st) {
+static int launch_tc(const st2_conv_args& a, const void* wtc, int mode, int max_ctas, cudaStream_t st) {
   const int n_tq = cdiv(a.Lq, TN), n_cob = cdiv(a.Cout, TM), ncb = cdiv(a.Cin, CB);
   const int rw = (TN + (a.K - 1) * a.dil + 7) & ~7;
   const int ntiles = a.B * n_cob * n_tq;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+  static int num_sms[64] = {0};   // per device ordinal (cudaFuncSetAttribute is per device too)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!num_sms[dev]) {
+    cudaDeviceGetAttribute(&num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(conv1d_tc_kernel<MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    cudaFuncSetAttribute(conv1d_tc_kernel<MODE_ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    cudaFuncSetAttribute(conv1d_tc_kernel<MODE_X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
   }
-  int grid = ntiles < num_sms ? ntiles : num_sms;
+  int grid = ntiles < num_sms[dev] ? ntiles : num_sms[dev];
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  conv1d_tc_kernel<<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
+  if (mode == MODE_FAST) conv1d_tc_kernel<MODE_FAST><<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
+  else if (mode == MODE_ACC) conv1d_tc_kernel<MODE_ACC><<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
+  else conv1d_tc_kernel<MODE_X3><<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
   ++g_launches;
   return 0;
 }
@@ -603,10 +742,12 @@ long long st2_conv_tc_weight_bytes(int Cout, int Cin, int K) {
   return (long long)K * n_cob * ncb * tc::W_STAGE_BYTES;
 }
 
-int st2_conv_tc_weight_layout(const float* w, void* out, int Cout, int Cin, int K, void* stream) {
-  ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0, "st2_conv_tc_weight_layout", "bad args");
+static bool tc_mode_ok(int mode) { return mode == ST2_TC_FAST || mode == ST2_TC_ACCURATE || mode == ST2_TC_F16X3; }
+
+int st2_conv_tc_weight_layout(const float* w, void* out, int Cout, int Cin, int K, int mode, void* stream) {
+  ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0 && tc_mode_ok(mode), "st2_conv_tc_weight_layout", "bad args");
   const int n_cob = cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB);
-  tc::conv_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out, Cout, Cin, K, n_cob, ncb);
+  tc::conv_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)out, Cout, Cin, K, n_cob, ncb, mode);
   ++g_launches;
   ST2_CHECK_LAUNCH("st2_conv_tc_weight_layout");
   return 0;
@@ -617,13 +758,13 @@ int st2_conv_tc_supported(int Cin, int Cout, int K, int stride, int dil) {
   return stride == 1 && rw <= tc::RW_MAX && cdiv(Cin, tc::CB) * tc::CB <= tc::CIN_PAD_MAX;
 }
 
-int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int max_ctas, void* stream) {
-  ST2_REQUIRE(a && a->x && wtc && a->y, "st2_conv1d_tc", "null pointer");
+int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int mode, int max_ctas, void* stream) {
+  ST2_REQUIRE(a && a->x && wtc && a->y && tc_mode_ok(mode), "st2_conv1d_tc", "null pointer / bad mode");
   ST2_REQUIRE(st2_conv_tc_supported(a->Cin, a->Cout, a->K, a->stride, a->dil), "st2_conv1d_tc", "unsupported shape");
   ST2_REQUIRE(a->pre_act != ST2_ACT_SNAKE || a->pre_alpha, "st2_conv1d_tc", "snake prologue needs alpha");
   const int n_tq = cdiv(a->Lq, tc::TN);
   ST2_REQUIRE(!a->stats || a->stats_nparts >= a->stats_part_offset + 2 * n_tq, "st2_conv1d_tc", "stats buffer too small (2 partials per 256-column tile)");
-  tc::launch_tc(*a, wtc, max_ctas, (cudaStream_t)stream);
+  tc::launch_tc(*a, wtc, mode, max_ctas, (cudaStream_t)stream);
   ST2_CHECK_LAUNCH("st2_conv1d_tc");
   return 0;
 }
@@ -640,18 +781,18 @@ long long st2_convT_tc_weight_bytes(int Cin, int Cout, int K, int S) {
   return (long long)S * st2_conv_tc_weight_bytes(Cout, Cin, J);
 }
 
-int st2_convT_tc_weight_layout(const float* w, void* out, int Cin, int Cout, int K, int S, int P, void* stream) {
-  ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0 && S > 0, "st2_convT_tc_weight_layout", "bad args");
+int st2_convT_tc_weight_layout(const float* w, void* out, int Cin, int Cout, int K, int S, int P, int mode, void* stream) {
+  ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0 && S > 0 && tc_mode_ok(mode), "st2_convT_tc_weight_layout", "bad args");
   const int J = (K + S - 1) / S;
   const int n_cob = cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB);
-  tc::convT_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)out, Cin, Cout, K, S, P, J, n_cob, ncb);
+  tc::convT_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)out, Cin, Cout, K, S, P, J, n_cob, ncb, mode);
   ++g_launches;
   ST2_CHECK_LAUNCH("st2_convT_tc_weight_layout");
   return 0;
 }
 
-int st2_conv_transpose1d_tc(const st2_conv_args* a0, const void* wtc, int K, int S, int P, int reflect_left1, void* stream) {
-  ST2_REQUIRE(a0 && a0->x && wtc && a0->y, "st2_conv_transpose1d_tc", "null pointer");
+int st2_conv_transpose1d_tc(const st2_conv_args* a0, const void* wtc, int mode, int K, int S, int P, int reflect_left1, void* stream) {
+  ST2_REQUIRE(a0 && a0->x && wtc && a0->y && tc_mode_ok(mode), "st2_conv_transpose1d_tc", "null pointer / bad mode");
   ST2_REQUIRE(K > 0 && S > 0 && P >= 0, "st2_conv_transpose1d_tc", "bad shape");
   const int J = (K + S - 1) / S;
   ST2_REQUIRE(st2_conv_tc_supported(a0->Cin, a0->Cout, J, 1, 1), "st2_conv_transpose1d_tc", "unsupported shape");
@@ -671,7 +812,7 @@ int st2_conv_transpose1d_tc(const st2_conv_args* a0, const void* wtc, int K, int
     a.y_len = a0->Lin * S + (reflect_left1 ? 1 : 0);
     a.stats_part_offset = r * parts;
     a.dup_q0_to = (reflect_left1 && r == 1) ? 0 : -1;
-    tc::launch_tc(a, (const uint8_t*)wtc + (size_t)r * phase_bytes, 0, (cudaStream_t)stream);
+    tc::launch_tc(a, (const uint8_t*)wtc + (size_t)r * phase_bytes, mode, 0, (cudaStream_t)stream);
   }
   ST2_CHECK_LAUNCH("st2_conv_transpose1d_tc");
   return 0;

@@ -33,9 +33,15 @@ __global__ void embedding_sum_rows_kernel(const long long* __restrict__ tokens, 
 }
 
 __global__ void durations_kernel(const float* __restrict__ logits, int rows, int N, int J, int last_plus,
-                                 int* __restrict__ pred, float* __restrict__ dur_f) {
+                                 const int* __restrict__ lengths, int* __restrict__ pred, float* __restrict__ dur_f) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
+  const int len = lengths ? lengths[r / N] : N;   // padded tokens (n >= len) emit no frames
+  if ((r % N) >= len) {
+    pred[r] = 0;
+    if (dur_f) dur_f[r] = 0.f;
+    return;
+  }
   const float* lp = logits + (long long)r * J;
   double s = 0.0;
   for (int j = 0; j < J; ++j) s += (double)sigmoidf_(lp[j]);
@@ -44,7 +50,7 @@ __global__ void durations_kernel(const float* __restrict__ logits, int rows, int
   float rd = rintf(d);  // torch.round: half to even
   if (rd < 1.f) rd = 1.f;
   int v = (int)rd;
-  if ((r % N) == N - 1) v += last_plus;
+  if ((r % N) == len - 1) v += last_plus;   // pred_dur[-1] += 5 of the single-speaker notebook: the LAST REAL token
   pred[r] = v;
 }
 
@@ -170,9 +176,10 @@ int st2_embedding_sum_rows(const long long* tokens, const float* word, const flo
   return 0;
 }
 
-int st2_durations(const float* logits, int B, int N, int J, int last_plus, int* pred_dur, float* dur_f, void* stream) {
+int st2_durations(const float* logits, int B, int N, int J, int last_plus, const int* lengths, int* pred_dur, float* dur_f,
+                  void* stream) {
   ST2_REQUIRE(logits && pred_dur && B > 0 && N > 0 && J > 0, "st2_durations", "bad args");
-  durations_kernel<<<cdiv(B * N, 128), 128, 0, (cudaStream_t)stream>>>(logits, B * N, N, J, last_plus, pred_dur, dur_f);
+  durations_kernel<<<cdiv(B * N, 128), 128, 0, (cudaStream_t)stream>>>(logits, B * N, N, J, last_plus, lengths, pred_dur, dur_f);
   ++g_launches;
   ST2_CHECK_LAUNCH("st2_durations");
   return 0;

@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libstyletts2_b200.so")
 
 ACT_NONE, ACT_LRELU, ACT_SNAKE, ACT_TANH, ACT_GELU, ACT_GELU_TANH = 0, 1, 2, 3, 4, 5
+TC_FAST, TC_ACCURATE, TC_F16X3 = 0, 1, 2      # precision recipes of the tensor-core conv (include/styletts2_b200.h)
+ABI_VERSION = 2
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
@@ -64,13 +66,13 @@ SIGNATURES = {
     "st2_conv1d": [C.POINTER(ConvArgs), _vp],
     "st2_conv_stats_parts": [_i],
     "st2_conv_tc_weight_bytes": [_i, _i, _i],
-    "st2_conv_tc_weight_layout": [_vp, _vp, _i, _i, _i, _vp],
+    "st2_conv_tc_weight_layout": [_vp, _vp, _i, _i, _i, _i, _vp],
     "st2_conv_tc_supported": [_i, _i, _i, _i, _i],
-    "st2_conv1d_tc": [C.POINTER(ConvArgs), _vp, _i, _vp],
+    "st2_conv1d_tc": [C.POINTER(ConvArgs), _vp, _i, _i, _vp],
     "st2_debug_set_trace": [_vp],
     "st2_convT_tc_weight_bytes": [_i, _i, _i, _i],
-    "st2_convT_tc_weight_layout": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "st2_conv_transpose1d_tc": [C.POINTER(ConvArgs), _vp, _i, _i, _i, _i, _vp],
+    "st2_convT_tc_weight_layout": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "st2_conv_transpose1d_tc": [C.POINTER(ConvArgs), _vp, _i, _i, _i, _i, _i, _vp],
     "st2_conv_transpose1d": [C.POINTER(ConvArgs), _vp, _i, _i, _i, _i, _vp],
     "st2_instance_stats": [_vp, _ll, _i, _i, _i, _vp, _vp],
     "st2_adain_coef": [_vp, _i, _vp, _ll, _i, _i, _f, _vp, _vp, _vp],
@@ -95,7 +97,7 @@ SIGNATURES = {
     "st2_time_embedding": [_vp, _vp, _i, _i, _vp, _ll, _vp],
     "st2_axpby": [_vp, _f, _vp, _f, _vp, _i, _vp],
     "st2_embedding_cl": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp],
-    "st2_durations": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "st2_durations": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "st2_frame_tokens": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "st2_expand_rows": [_vp, _ll, _vp, _i, _i, _i, _i, _vp, _ll, _vp],
     "st2_expand_cl": [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp],
@@ -136,7 +138,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.st2_abi_version() != 1:
+    if lib.st2_abi_version() != ABI_VERSION:
         raise RuntimeError("styletts2_b200 ABI version mismatch")
     _lib = lib
     return lib

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .lib import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SNAKE, ACT_TANH
+from .lib import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SNAKE, ACT_TANH, TC_ACCURATE, TC_FAST
 
 
 # =========================================================================== parameter holders
@@ -54,7 +54,7 @@ class WNConv1d(_Cached):
 
     def _prepare(self):
         w = ops.fold_weight_norm(self.weight_v, self.weight_g)
-        return ops.conv_weight_layout(w), w, _maybe_wtc(w, self.stride, self.dilation)
+        return ops.conv_weight_layout(w), w, _maybe_wtc(w, self.stride, self.dilation, getattr(self, "tc_mode", TC_FAST))
 
     def wt(self):
         return self.prepared()[0]
@@ -71,12 +71,21 @@ class WNConv1d(_Cached):
         return y
 
 
-def _maybe_wtc(w, stride, dilation):
-    """bf16 hi/lo tensor-core weight blocks when the tcgen05 conv supports the shape and it is worth it."""
+def _maybe_wtc(w, stride, dilation, mode=TC_FAST):
+    """plane-split tensor-core weight blocks when the tcgen05 conv supports the shape and it is worth it.
+    mode: precision recipe (TC_FAST for the decoder / vocoder, TC_ACCURATE for the F0/N predictor)."""
     co, ci, k = w.shape
     if stride == 1 and co >= 16 and ci >= 16 and ops.conv_tc_supported(ci, co, k, stride, dilation):
-        return ops.conv_tc_weight_layout(w)
+        return ops.conv_tc_weight_layout(w, mode)
     return None
+
+
+def set_tc_mode(root: nn.Module, mode: int):
+    """Select the tensor-core precision recipe of every conv below `root` (before its weights are first prepared)."""
+    for m in root.modules():
+        if isinstance(m, (WNConv1d, Conv1d, WNConvTranspose1d)):
+            m.tc_mode = mode
+            m.__dict__.pop("_prep", None)
 
 
 class Conv1d(_Cached):
@@ -89,7 +98,7 @@ class Conv1d(_Cached):
         self.bias = nn.Parameter(torch.zeros(cout))
 
     def _prepare(self):
-        return ops.conv_weight_layout(self.weight), _maybe_wtc(self.weight.detach(), self.stride, 1)
+        return ops.conv_weight_layout(self.weight), _maybe_wtc(self.weight.detach(), self.stride, 1, getattr(self, "tc_mode", TC_FAST))
 
     def wt(self):
         return self.prepared()[0]
@@ -119,7 +128,7 @@ class WNConvTranspose1d(_Cached):
             J = (self.k + self.stride - 1) // self.stride
             wtc = None
             if self.cin >= 16 and self.cout >= 16 and ops.conv_tc_supported(self.cin, self.cout, J, 1, 1):
-                wtc = ops.convT_tc_weight_layout(w, self.stride, self.padding)
+                wtc = ops.convT_tc_weight_layout(w, self.stride, self.padding, getattr(self, "tc_mode", TC_FAST))
             return ops.convT_weight_layout(w, self.stride, self.padding), w, wtc
         return None, w.contiguous(), None
 
@@ -442,6 +451,9 @@ class ProsodyPredictor(nn.Module):
         self.F0_proj = Conv1d(d_hid // 2, 1, 1, 1, 0)
         self.N_proj = Conv1d(d_hid // 2, 1, 1, 1, 0)
         self.d_hid = d_hid
+        # F0 is integrated into a phase of 1e4..1e6 rad by the harmonic source downstream: this subtree runs the
+        # fp32-accurate tensor-core recipe (two fp16 planes, separate correction accumulator)
+        set_tc_mode(self, TC_ACCURATE)
 
     def forward(self, texts, style, text_lengths, alignment, m):
         d = self.text_encoder(texts, style, text_lengths, m)
@@ -457,6 +469,10 @@ class ProsodyPredictor(nn.Module):
         C = self.d_hid
         h = ops.empty(B, C, T, device=dev)
         xt = x.transpose(-1, -2)
+        if xt.stride(2) != 1:
+            # conv-layout input (the notebooks' `d.transpose(-1,-2) @ pred_aln_trg`): one transposing copy, so that the
+            # LSTM input projection runs the same row-layout GEMM (same bits) whichever way the caller built `en`
+            xt = xt.contiguous()
         self.shared.run(xt, B, T, xt.stride(), h, (C * T, 1, T))
         fcs = StyleFC(self, s.contiguous())
         hst = ops.instance_stats(h)

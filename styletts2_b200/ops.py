@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import lib as L
-from .lib import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SNAKE, ACT_TANH, ConvArgs, RowsArgs, ptr, stream_ptr
+from .lib import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SNAKE, ACT_TANH, TC_ACCURATE, TC_FAST, TC_F16X3, ConvArgs, RowsArgs, ptr, stream_ptr
 
 f32 = torch.float32
 
@@ -86,7 +86,35 @@ def _fill_conv_args(a: ConvArgs, x, wt, bias, y, *, K, stride, dil, pad, Lq, y_l
     a.dup_q0_to = -1
 
 
-PROFILE = None  # bench.py sets this to a list to collect (name, algorithmic_flops, algorithmic_bytes, ev0, ev1) per TC conv launch
+PROFILE = None  # bench.py sets this to a list: (name, algorithmic_flops, algorithmic_bytes, ev0, ev1, mma_per_product) per launch
+NVTX = os.environ.get("ST2_NVTX", "0") != "0"   # NVTX range per kernel family / stage (nsys / ncu --nvtx)
+
+
+class _prof:
+    """CUDA events around one launch (or launch group) when bench.py profiling is on; NVTX range when ST2_NVTX=1."""
+    __slots__ = ("name", "flops", "nbytes", "nmma", "e0")
+
+    def __init__(self, name, flops=0.0, nbytes=0.0, nmma=0):
+        self.name, self.flops, self.nbytes, self.nmma, self.e0 = name, flops, nbytes, nmma, None
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name.split(" ")[0])
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.flops, self.nbytes, self.e0, e1, self.nmma))
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 USE_TC = os.environ.get("ST2_TC", "1") != "0"   # tensor-core (tcgen05) conv path where a wtc buffer is given
 TC_MIN_WORK = 1 << 22                            # below this many MACs per utterance the SIMT kernel is used
 
@@ -95,14 +123,30 @@ def conv_tc_supported(Cin, Cout, K, stride, dil) -> bool:
     return bool(L.load().st2_conv_tc_supported(Cin, Cout, K, stride, dil))
 
 
-def conv_tc_weight_layout(w: torch.Tensor) -> torch.Tensor:
-    """folded fp32 [Cout,Cin,K] -> bf16 hi/lo stage blocks for st2_conv1d_tc (opaque uint8 buffer)"""
+class TCWeights:
+    """Tensor-core weight blocks of one conv (opaque uint8 buffer) + the precision recipe they were laid out for."""
+    __slots__ = ("buf", "mode")
+
+    def __init__(self, buf, mode):
+        self.buf, self.mode = buf, int(mode)
+
+
+TC_MODE_OVERRIDE = os.environ.get("ST2_TC_MODE")   # A/B testing: force one recipe ("0" fast, "1" accurate, "2" f16x3)
+
+
+def _tc_mode(mode):
+    return int(TC_MODE_OVERRIDE) if TC_MODE_OVERRIDE is not None else int(mode)
+
+
+def conv_tc_weight_layout(w: torch.Tensor, mode: int = TC_FAST) -> TCWeights:
+    """folded fp32 [Cout,Cin,K] -> plane-split stage blocks for st2_conv1d_tc"""
     w = w.detach().contiguous()
     co, ci, k = w.shape
+    mode = _tc_mode(mode)
     nbytes = int(L.load().st2_conv_tc_weight_bytes(co, ci, k))
     out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    L.call("st2_conv_tc_weight_layout", ptr(w), ptr(out), co, ci, k, stream_ptr())
-    return out
+    L.call("st2_conv_tc_weight_layout", ptr(w), ptr(out), co, ci, k, mode, stream_ptr())
+    return TCWeights(out, mode)
 
 
 def conv1d(x, wt, bias=None, *, K, stride=1, dil=1, pad=0, pre=None, pre_act=ACT_NONE, slope=0.0, alpha=None,
@@ -126,28 +170,26 @@ def conv1d(x, wt, bias=None, *, K, stride=1, dil=1, pad=0, pre=None, pre_act=ACT
     _fill_conv_args(a, x, wt, bias, out, K=K, stride=stride, dil=dil, pad=pad, Lq=Lout, y_len=Lout, pre=pre,
                     pre_act=pre_act, slope=slope, alpha=alpha, res=res, res_shift=res_shift, out_div=out_div,
                     accum_mode=accum_mode, accum_div=accum_div, out_act=out_act, stats=stats, nparts=nparts)
+    nbytes = 4.0 * B * (Lin * Cin + Lout * Cout * ((2 if res is not None else 1) + (1 if accum_mode else 0)))
+    flops = 2.0 * B * Cin * Cout * K * Lout
     if use_tc:
-        if PROFILE is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        L.call("st2_conv1d_tc", C.byref(a), ptr(wtc), tc_max_ctas, stream_ptr())
-        if PROFILE is not None:
-            e1.record()
-            nbytes = 4.0 * B * Lout * (Cin + Cout * (2 if res is not None else 1) + (Cout if accum_mode else 0))
-            PROFILE.append((f"conv1d_tc ci{Cin} co{Cout} k{K} d{dil} L{Lout} B{B}", 2.0 * B * Cin * Cout * K * Lout, nbytes, e0, e1))
+        with _prof(f"conv1d_tc m{wtc.mode} ci{Cin} co{Cout} k{K} d{dil} L{Lout} B{B}", flops, nbytes, 2 if wtc.mode == TC_FAST else 3):
+            L.call("st2_conv1d_tc", C.byref(a), ptr(wtc.buf), wtc.mode, tc_max_ctas, stream_ptr())
     else:
-        L.call("st2_conv1d", C.byref(a), stream_ptr())
+        with _prof(f"conv1d_simt ci{Cin} co{Cout} k{K} s{stride} L{Lout} B{B}", flops, nbytes):
+            L.call("st2_conv1d", C.byref(a), stream_ptr())
     return out, stats
 
 
-def convT_tc_weight_layout(w: torch.Tensor, stride: int, padding: int) -> torch.Tensor:
+def convT_tc_weight_layout(w: torch.Tensor, stride: int, padding: int, mode: int = TC_FAST) -> TCWeights:
     """folded fp32 ConvTranspose1d weight [Cin,Cout,K] -> per-phase tensor-core blocks"""
     w = w.detach().contiguous()
     ci, co, k = w.shape
+    mode = _tc_mode(mode)
     nbytes = int(L.load().st2_convT_tc_weight_bytes(ci, co, k, stride))
     out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-    L.call("st2_convT_tc_weight_layout", ptr(w), ptr(out), ci, co, k, stride, padding, stream_ptr())
-    return out
+    L.call("st2_convT_tc_weight_layout", ptr(w), ptr(out), ci, co, k, stride, padding, mode, stream_ptr())
+    return TCWeights(out, mode)
 
 
 def conv_transpose1d(x, wp, bias, *, K, stride, padding, pre_act=ACT_NONE, slope=0.0, alpha=None, res=None,
@@ -168,10 +210,15 @@ def conv_transpose1d(x, wp, bias, *, K, stride, padding, pre_act=ACT_NONE, slope
     _fill_conv_args(a, x, wp, bias, out, K=1, stride=1, dil=1, pad=0, Lq=Lin, y_len=Lout, pre=None, pre_act=pre_act,
                     slope=slope, alpha=alpha, res=res, res_shift=0, out_div=1.0, accum_mode=0, accum_div=1.0,
                     out_act=ACT_NONE, stats=stats, nparts=nparts)
+    J = (K + S - 1) // S
+    nbytes = 4.0 * B * (Lin * Cin + Lout * Cout * (2 if res is not None else 1))
+    flops = 2.0 * B * Cin * Cout * J * S * Lin
     if use_tc:
-        L.call("st2_conv_transpose1d_tc", C.byref(a), ptr(wtc), K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
+        with _prof(f"convT_tc m{wtc.mode} ci{Cin} co{Cout} k{K} s{S} L{Lin} B{B}", flops, nbytes, 2 if wtc.mode == TC_FAST else 3):
+            L.call("st2_conv_transpose1d_tc", C.byref(a), ptr(wtc.buf), wtc.mode, K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
     else:
-        L.call("st2_conv_transpose1d", C.byref(a), ptr(wp), K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
+        with _prof(f"convT_simt ci{Cin} co{Cout} k{K} s{S} L{Lin} B{B}", flops, nbytes):
+            L.call("st2_conv_transpose1d", C.byref(a), ptr(wp), K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
     return out, stats
 
 
@@ -179,7 +226,8 @@ def instance_stats(x) -> torch.Tensor:
     x = _cl(x)
     B, Cc, Ln = x.shape
     st = empty(B, Cc, 1, 3, device=x.device)
-    L.call("st2_instance_stats", ptr(x), x.stride(0), B, Cc, Ln, ptr(st), stream_ptr())
+    with _prof(f"instance_stats c{Cc} L{Ln} B{B}", 0.0, 4.0 * B * Cc * Ln):
+        L.call("st2_instance_stats", ptr(x), x.stride(0), B, Cc, Ln, ptr(st), stream_ptr())
     return st
 
 
@@ -197,8 +245,9 @@ def adain_lrelu_pool(x, a, b, pool_w, pool_b, slope=0.2):
     x = _cl(x)
     B, Cc, Ln = x.shape
     y = empty(B, Cc, 2 * Ln, device=x.device)
-    L.call("st2_adain_lrelu_pool", ptr(x), x.stride(0), ptr(a), ptr(b), ptr(pool_w), ptr(pool_b), slope, B, Cc, Ln,
-           ptr(y), y.stride(0), stream_ptr())
+    with _prof(f"adain_lrelu_pool c{Cc} L{Ln} B{B}", 0.0, 4.0 * B * Cc * Ln * 3):
+        L.call("st2_adain_lrelu_pool", ptr(x), x.stride(0), ptr(a), ptr(b), ptr(pool_w), ptr(pool_b), slope, B, Cc, Ln,
+               ptr(y), y.stride(0), stream_ptr())
     return y
 
 
@@ -286,16 +335,18 @@ def linear(A, W, bias=None, *, act=ACT_NONE, R=None, out=None, wtc=None):
         R2, Mr, ldr = _rows_view(R)
         assert R2.data_ptr() == R.data_ptr() and Mr == M
     if wtc is not None and USE_TC and M >= LINEAR_TC_MIN_ROWS:
-        if Nf > 128 and LINEAR_TC_PRESPLIT:
-            # split the activation rows into fp16 operand stages once (not once per 128-feature output block inside the GEMM)
-            planes = torch.empty(int(L.load().st2_linear_tc_split_bytes(M, K)), dtype=torch.uint8, device=A.device)
-            L.call("st2_linear_tc_split", ptr(A2), lda, M, K, ptr(planes), stream_ptr())
-            L.call("st2_linear_tc_pre", ptr(A2), lda, ptr(planes), ptr(wtc), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act,
-                   stream_ptr())
-        else:
-            L.call("st2_linear_tc", ptr(A2), lda, ptr(wtc), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
+        with _prof(f"linear_tc M{M} N{Nf} K{K}", 2.0 * M * Nf * K, 4.0 * (M * K + Nf * K + M * Nf * (2 if R is not None else 1)), 3):
+            if Nf > 128 and LINEAR_TC_PRESPLIT:
+                # split the activation rows into fp16 operand stages once (not once per 128-feature output block inside the GEMM)
+                planes = torch.empty(int(L.load().st2_linear_tc_split_bytes(M, K)), dtype=torch.uint8, device=A.device)
+                L.call("st2_linear_tc_split", ptr(A2), lda, M, K, ptr(planes), stream_ptr())
+                L.call("st2_linear_tc_pre", ptr(A2), lda, ptr(planes), ptr(wtc), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act,
+                       stream_ptr())
+            else:
+                L.call("st2_linear_tc", ptr(A2), lda, ptr(wtc), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
     else:
-        L.call("st2_linear", ptr(A2), 0, lda, 1, M, ptr(W), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
+        with _prof(f"linear_simt M{M} N{Nf} K{K}", 2.0 * M * Nf * K, 4.0 * (M * K + Nf * K + M * Nf)):
+            L.call("st2_linear", ptr(A2), 0, lda, 1, M, ptr(W), ptr(bias), ptr(R), ldr, ptr(out), ldc, M, Nf, K, act, stream_ptr())
     return out
 
 
@@ -312,13 +363,15 @@ def linear_strided(x, B, Lr, K, bs, ls, ks, W, bias=None, *, act=ACT_NONE, out=N
 
 def attention(q, kv, B, N, H=8, D=64):
     out = empty(B * N, H * D, device=q.device)
-    L.call("st2_attention", ptr(q), ptr(kv), ptr(out), B, N, H, D, float(D) ** -0.5, stream_ptr())
+    with _prof(f"attention B{B} N{N} H{H} D{D}", 4.0 * B * H * N * N * D, 4.0 * B * N * H * D * 4):
+        L.call("st2_attention", ptr(q), ptr(kv), ptr(out), B, N, H, D, float(D) ** -0.5, stream_ptr())
     return out
 
 
 def lstm_bidir(gx, whh, out, o_bs, o_ts, o_cs, B, Lr, H, lengths=None):
     work = empty(6 * B * H + 64, device=gx.device)
-    L.call("st2_lstm_bidir", ptr(gx), ptr(whh), ptr(out), o_bs, o_ts, o_cs, ptr(lengths), B, Lr, H, ptr(work), stream_ptr())
+    with _prof(f"lstm_bidir B{B} L{Lr} H{H}", 16.0 * B * Lr * H * H, 0.0):
+        L.call("st2_lstm_bidir", ptr(gx), ptr(whh), ptr(out), o_bs, o_ts, o_cs, ptr(lengths), B, Lr, H, ptr(work), stream_ptr())
     return out
 
 
@@ -359,11 +412,12 @@ def embedding_cl(tokens, table, lengths=None):
     return out
 
 
-def durations(logits, last_plus=0):
+def durations(logits, last_plus=0, lengths=None):
+    """lengths [B] int32 (optional): padded tokens get duration 0, `last_plus` lands on the last real token."""
     B, N, J = logits.shape
     pred = torch.empty(B, N, device=logits.device, dtype=torch.int32)
     durf = empty(B, N, device=logits.device)
-    L.call("st2_durations", ptr(logits.contiguous()), B, N, J, last_plus, ptr(pred), ptr(durf), stream_ptr())
+    L.call("st2_durations", ptr(logits.contiguous()), B, N, J, last_plus, ptr(lengths), ptr(pred), ptr(durf), stream_ptr())
     return pred, durf
 
 
@@ -444,8 +498,10 @@ def sine_source(f0, scale_, noise, lin_w, lin_b):
     out = empty(B, F * scale_, device=f0.device)
     work = empty(B * 9 * F, device=f0.device)
     seed, off = (0, 0) if noise is not None else _rng_take(B * F * scale_ * 3)
-    L.call("st2_sine_source", ptr(f0), B, F, scale_, ptr(noise.contiguous() if noise is not None else None), ptr(lin_w.contiguous()),
-           ptr(lin_b), ptr(out), ptr(work), seed, off, ptr(_rng_epoch(f0.device)) if noise is None else None, stream_ptr())
+    with _prof(f"sine_source F{F} x{scale_} B{B}", 0.0, 4.0 * B * F * scale_ * (1 + (9 if noise is not None else 0))):
+        L.call("st2_sine_source", ptr(f0), B, F, scale_, ptr(noise.contiguous() if noise is not None else None),
+               ptr(lin_w.contiguous()), ptr(lin_b), ptr(out), ptr(work), seed, off,
+               ptr(_rng_epoch(f0.device)) if noise is None else None, stream_ptr())
     return out
 
 
@@ -453,7 +509,8 @@ def stft20(x):
     x = x.contiguous()
     B, Ln = x.shape
     har = empty(B, 22, Ln // 5 + 1, device=x.device)
-    L.call("st2_stft20", ptr(x), B, Ln, ptr(har), stream_ptr())
+    with _prof(f"stft20 L{Ln} B{B}", 0.0, 4.0 * B * (Ln + 22 * (Ln // 5 + 1))):
+        L.call("st2_stft20", ptr(x), B, Ln, ptr(har), stream_ptr())
     return har
 
 
@@ -461,7 +518,8 @@ def istft20_expsin(x):
     x = x.contiguous()
     B, _, Fr = x.shape
     wav = empty(B, 5 * (Fr - 1), device=x.device)
-    L.call("st2_istft20_expsin", ptr(x), B, Fr, ptr(wav), stream_ptr())
+    with _prof(f"istft20 F{Fr} B{B}", 0.0, 4.0 * B * (22 * Fr + 5 * (Fr - 1))):
+        L.call("st2_istft20_expsin", ptr(x), B, Fr, ptr(wav), stream_ptr())
     return wav
 
 

@@ -18,10 +18,12 @@ def shard_range(batch: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def plan_equal_length_batches(lengths: Sequence[int], world: int, max_batch: int) -> List[List[List[int]]]:
-    """Serving-side plan for a queue of utterances with DIFFERENT token counts (host part only): the
-    batched engine needs equal-length batches (Synthesizer.synthesize), so utterances are bucketed by token count, cut into
-    batches of at most `max_batch`, and the batches are dealt to ranks longest-processing-time first (cost ~ tokens x
-    utterances) so that every GPU finishes at about the same time.  Deterministic (ties by first utterance index).
+    """Serving-side plan for a queue of utterances with DIFFERENT token counts (host part): utterances
+    are bucketed by token count (no token padding inside a batch), cut into batches of at most `max_batch`, and the
+    batches are dealt to ranks longest-processing-time first (cost ~ tokens x utterances) so that every GPU finishes at
+    about the same time.  Equal token counts do NOT imply equal predicted frame counts: Synthesizer.synthesize groups
+    each batch by total duration after the duration kernel and runs one launch chain per distinct length (the text
+    side -- PL-BERT, text encoder, sampler, duration predictor -- stays batched).  Deterministic (ties by first index).
     Returns plan[rank] = list of batches, each a list of utterance indices."""
     assert world >= 1 and max_batch >= 1
     buckets: Dict[int, List[int]] = {}
@@ -52,16 +54,26 @@ def init_from_env(backend: str = "nccl"):
     return rank, local, world
 
 
-def gather_waveforms(wav_local: torch.Tensor, world: int, dst: int = 0):
-    """Optional final collective: gather [B/G, L] fp32 waveforms on `dst` (NCCL over NVLink on GPUs,
-    gloo in the CPU tests).  Returns the list of shards on dst, None elsewhere."""
+def gather_waveforms(wav_local: torch.Tensor, world: int, dst: int = 0, batch: int = None):
+    """Optional final collective: gather the shard waveforms [B_r, L] (fp32) on `dst` (NCCL over NVLink on GPUs, gloo in
+    the CPU tests).  Shards may be UNEVEN (shard_range gives the first batch % world ranks one utterance more): every
+    rank pads its shard to the largest one, `dist.gather` moves equal-sized buffers to `dst` only, and `dst` slices the
+    padding off.  `batch` = global utterance count when the shards came from shard_range(batch, r, world); None = every
+    rank holds wav_local.shape[0] utterances.  Returns the list of shards on dst, None elsewhere."""
     if world == 1:
         return [wav_local]
-    rank = torch.distributed.get_rank()
-    if torch.distributed.get_backend() == "nccl":
-        out = [torch.empty_like(wav_local) for _ in range(world)]
-        torch.distributed.all_gather(out, wav_local.contiguous())
-        return out if rank == dst else None
-    bufs = [torch.empty_like(wav_local) for _ in range(world)] if rank == dst else None
-    torch.distributed.gather(wav_local.contiguous(), bufs, dst=dst)
-    return bufs
+    dist = torch.distributed
+    rank = dist.get_rank()
+    sizes = [wav_local.shape[0]] * world if batch is None else [shard_range(batch, r, world)[1] - shard_range(batch, r, world)[0]
+                                                                 for r in range(world)]
+    assert sizes[rank] == wav_local.shape[0], (sizes, rank, tuple(wav_local.shape))
+    big = max(sizes)
+    send = wav_local.contiguous()
+    if send.shape[0] < big:
+        pad = torch.zeros((big - send.shape[0],) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        send = torch.cat([send, pad], 0)
+    bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, bufs, dst=dst)
+    if rank != dst:
+        return None
+    return [b[:n] for b, n in zip(bufs, sizes)]

@@ -111,7 +111,7 @@ def test_c_abi_library_exports_every_declared_symbol(lib_built):
     for name in declared:
         assert hasattr(so, name), name
     lib = L.load()
-    assert lib.st2_abi_version() == 1
+    assert lib.st2_abi_version() == L.ABI_VERSION == 2
     assert L.launch_count() == 0
 
 

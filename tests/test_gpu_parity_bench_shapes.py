@@ -1,0 +1,109 @@
+"""GPU tier: parity AT THE SHAPES THE BENCHMARK RUNS (BASELINE.json configs[1], [2] per GPU, [3]):
+  C2  LJSpeech / iSTFTNet   B=32, N=128, T=512,  K=5
+  C3  LibriTTS / HiFi-GAN   B=8 (per GPU), N=128, T=512, K=10
+  C4  LJSpeech / iSTFTNet   B=16, N=500, T=2000, K=5
+The engine runs the WHOLE batch exactly as bench.py does (same synthetic inputs, durations pinned to 4 frames per token
+after the duration kernel has run); the CPU oracle runs
+  * the text side (text encoder, sampler, duration predictor) on the whole batch: integer durations must be bit-exact on
+    all B*N tokens (4096 / 1024 / 8000), and the distance of every pre-rounding sum to the nearest rounding boundary is
+    recorded (guard-band statistics, SURVEY section 7 hard-part 2);
+  * the full path on TWO utterances of the batch alone (first and last; every op is per-utterance): F0 / N curves and --
+    with the oracle's F0/N (and har for iSTFTNet) teacher-forced for those two utterances only -- the waveform <= 1e-3.
+Tile tails (L = 61441, 240001), Cin = 1090, the 15-cluster LSTM grouping at B = 32 and 240 stats partials per row are
+all exercised here against the oracle, not only by the un-checked benchmark."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import cases
+import styletts2_oracle as O
+from util import gpu_model, maxdiff, oracle_sds, record
+
+D = "cuda:0"
+SHAPES = {
+    "C2": dict(model="ljspeech", B=32, N=128, fpt=4, K=5),
+    "C3": dict(model="libritts", B=8, N=128, fpt=4, K=10),
+    "C4": dict(model="ljspeech", B=16, N=500, fpt=4, K=5),
+}
+
+
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_bench_shape_parity(name):
+    from styletts2_b200.inference import Synthesizer
+    from styletts2_b200.synthetic import synthetic_batch
+    c = SHAPES[name]
+    model, B, N, fpt, K = c["model"], c["B"], c["N"], c["fpt"], c["K"]
+    ms = model == "libritts"
+    T, L = N * fpt, 600 * N * fpt
+    mcfg = cases.MODEL_CFGS[model]
+    m = gpu_model(model)
+    syn = Synthesizer(m, mcfg, D)
+    sds = oracle_sds(model)
+    tokens, lengths, bert_dur, noise, ref_s = synthetic_batch(B, N, ms, seed=1)      # == bench.py make_inputs(seed=1)
+    g = torch.Generator().manual_seed(4242)
+    steps = [torch.randn(B, 1, 256, generator=g) for _ in range(K - 1)]
+    picks = [0, B - 1]
+    sine = {b: torch.randn(1, L, 9, generator=torch.Generator().manual_seed(900 + b)) for b in picks}
+    sine_dev = torch.randn(B, L, 9, device=D, generator=torch.Generator(device=D).manual_seed(7))
+    for b in picks:
+        sine_dev[b].copy_(sine[b][0])
+    forced = torch.full((B, N), float(fpt))
+    dev_in = (tokens.to(D), lengths.to(D), bert_dur.to(D), noise.to(D))
+    common = dict(diffusion_steps=K, ref_s=None if ref_s is None else ref_s.to(D), forced_durations=forced, return_all=True)
+    inj = dict(step_noises=[s.to(D) for s in steps], sine_noise=sine_dev)
+    out = syn.synthesize(*dev_in, rng=inj, **common)
+    torch.cuda.synchronize()
+
+    # ---- 1. integer boundary over the whole batch
+    torch.set_num_threads(min(32, torch.get_num_threads() or 8))
+    with torch.no_grad():
+        front = O.synthesize(sds, mcfg, tokens, lengths, bert_dur, noise, diffusion_steps=K, ref_s=ref_s,
+                             rng=dict(step_noises=steps), front_only=True)
+    pd_ref = front["pred_dur"].to(torch.int32)
+    pd = out["pred_dur"].cpu()
+    nbad = int((pd != pd_ref).sum())
+    dur_f = front["dur_f"].double()
+    guard = (dur_f - torch.floor(dur_f) - 0.5).abs()           # distance to the nearest x.5 rounding boundary
+    hist = torch.histc(torch.log10(guard.clamp_min(1e-12)).float(), bins=8, min=-8, max=0).tolist()
+    dur_err = float((out["dur_f"].cpu().double() - dur_f).abs().max())
+    record("bench_shape_durations_" + name, tokens=B * N, mismatches=nbad, min_guard=float(guard.min()), duration_sum_maxabs_err=dur_err,
+           guard_log10_hist_1e-8_to_1=str([int(h) for h in hist]), s_pred_maxabs=maxdiff(out["s_pred"], front["s_pred"]),
+           logits_maxabs=maxdiff(out["logits"], front["logits"]))
+    assert nbad == 0, f"{nbad} of {B * N} integer durations differ (min guard band {float(guard.min()):.2e}, sum error {dur_err:.2e})"
+
+    # ---- 2. full path on two utterances alone
+    refs = {}
+    for b in picks:
+        sl = slice(b, b + 1)
+        with torch.no_grad():
+            refs[b] = O.synthesize(sds, mcfg, tokens[sl], lengths[sl], bert_dur[sl], noise[sl], diffusion_steps=K,
+                                   ref_s=None if ref_s is None else ref_s[sl],
+                                   rng=dict(step_noises=[s[sl] for s in steps], sine_noise=sine[b], rand_ini=torch.zeros(1, 9)),
+                                   forced_durations=forced[sl])
+    f0_err = max(maxdiff(out["F0"][b], refs[b]["F0"][0]) for b in picks)
+    f0_scale = max(float(refs[b]["F0"].abs().max()) for b in picks)
+    n_err = max(maxdiff(out["N"][b], refs[b]["N"][0]) for b in picks)
+    free = max(maxdiff(out["wav"][b, 0], refs[b]["wav"].reshape(-1)) for b in picks)
+    assert f0_err <= 1e-4 * max(1.0, f0_scale), (f0_err, f0_scale)
+    # teacher-force the oracle's prosody curves (and har) for the picked utterances; the rest of the batch keeps ours
+    F0i, Ni = out["F0"].clone(), out["N"].clone()
+    for b in picks:
+        F0i[b].copy_(refs[b]["F0"][0])
+        Ni[b].copy_(refs[b]["N"][0])
+    inj2 = dict(inj, F0=F0i, N=Ni)
+    if mcfg["decoder"]["type"] == "istftnet":
+        har = m.decoder.generator.har_features(F0i, sine_dev)
+        sdg = O.sub(sds["decoder"], "generator")
+        for b in picks:
+            with torch.no_grad():
+                har[b].copy_(O.istftnet_har(refs[b]["F0"], sdg, mcfg["decoder"], torch.zeros(1, 9), sine[b])[0])
+        inj2["har"] = har
+    out2 = syn.synthesize(*dev_in, rng=inj2, **common)
+    d = max(maxdiff(out2["wav"][b, 0], refs[b]["wav"].reshape(-1)) for b in picks)
+    scale = max(float(refs[b]["wav"].abs().max()) for b in picks)
+    record("bench_shape_wav_" + name, B=B, N=N, T=T, L=L, wav_maxabs_teacher_forced=d, wav_maxabs_free_running=free, wav_scale=scale,
+           F0_maxabs=f0_err, F0_scale=f0_scale, N_maxabs=n_err)
+    assert torch.isfinite(out["wav"]).all()
+    assert d <= 1e-3, d

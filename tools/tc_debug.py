@@ -13,7 +13,7 @@ def run(B, Cin, Cout, K, d, L, bias=True):
     pad = (K * d - d) // 2
     ref = F.conv1d(x, w, bs, 1, pad, d)
     wd = w.to(D)
-    y, _ = ops.conv1d(x.to(D), ops.conv_weight_layout(wd), None if bs is None else bs.to(D), K=K, dil=d, pad=pad, wtc=ops.conv_tc_weight_layout(wd))
+    y, _ = ops.conv1d(x.to(D), ops.conv_weight_layout(wd), None if bs is None else bs.to(D), K=K, dil=d, pad=pad, wtc=ops.conv_tc_weight_layout(wd, int(os.environ.get("ST2_TC_MODE", "0"))))
     torch.cuda.synchronize()
     y = y.cpu()
     err = (y - ref).abs()
