@@ -414,9 +414,12 @@ def cpu_reference(wl, sample_B, steps, warmup, probe=True):
     probe_res = {}
     best = min(32, ncpu)
     if probe:
-        for nt in sorted({min(8, ncpu), min(32, ncpu), ncpu}):
+        # one utterance per thread count (bounded: the probe must not eat the few minutes the default run has; all 128
+        # threads of the GPU box were measured 7x slower than 8 in round 1 -- oversubscribed intra-op pools -- and are
+        # probed only up to 64)
+        for nt in sorted({min(8, ncpu), min(16, ncpu), min(32, ncpu), min(64, ncpu)}):
             torch.set_num_threads(nt)
-            ts, ns = run(1, 2)
+            ts, ns = run(1, 1)
             probe_res[nt] = round(ns / ts[-1])
         best = max(probe_res, key=probe_res.get)
     torch.set_num_threads(best)

@@ -42,6 +42,9 @@ long long st2_launch_count(void);
  * (re-evaluated every forward by the reference: Modules/istftnet.py:30-46, models.py:293;
  * here folded once at load). */
 int st2_weight_norm_fold(const float* v, const float* g, float* w, int rows, int cols, void* stream);
+/* out[r] = ||v[r,:]||_2 with the fold kernel's own reduction: a folded weight w re-imported as (weight_v = w,
+ * weight_g = st2_row_norm(w)) folds back to exactly w (checkpoint export of folded weights, styletts2_b200/checkpoint.py) */
+int st2_row_norm(const float* v, float* out, int rows, int cols, void* stream);
 /* Conv1d weight [Cout,Cin,K] -> kernel layout [Cin][K][Cout] */
 int st2_conv_weight_layout(const float* w, float* wt, int Cout, int Cin, int K, void* stream);
 /* ConvTranspose1d weight [Cin,Cout,K] (stride S, padding P) -> polyphase layout
@@ -115,6 +118,9 @@ int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int mode, int max_cta
 /* Profiling aid: when set to a device buffer of 4*16*8 int64, CTA 0 of st2_conv1d_tc records per-role cycle
  * counters for its first 16 tiles (role 0 MMA, 1 weight producer, 2 stagers, 3 epilogue); NULL disables. */
 int st2_debug_set_trace(void* buf);
+/* Timing experiments only (tools/tc_bench.py): bit 0 second FAST MMA as kind::f16, bit 1 epilogue without global
+ * traffic, bit 2 stagers skip the conversion, bit 3 no MMAs.  Results are wrong while any bit is set; 0 restores. */
+int st2_debug_set_flags(int flags);
 /* Polyphase ConvTranspose1d on the same tensor-core kernel (one launch per phase); wtc from
  * st2_convT_tc_weight_layout (st2_convT_tc_weight_bytes bytes).  Arguments as st2_conv_transpose1d. */
 long long st2_convT_tc_weight_bytes(int Cin, int Cout, int K, int S);
@@ -275,6 +281,9 @@ int st2_stft20(const float* x, int B, int L, float* har, void* stream);
 /* conv_post tail + TorchSTFT.inverse (istftnet.py:378-380,99-104): x [B,22,Fr] ->
  * spec=exp(x[:11]), phase=sin(x[11:]) -> istft (n_fft 20, hop 5) -> wav [B, 5*(Fr-1)]. */
 int st2_istft20_expsin(const float* x, int B, int Fr, float* wav, void* stream);
+/* Wire format after the path (the notebooks hand the fp32 array to IPython.display.Audio /
+ * soundfile): out[i] = saturate_int16(rint(wav[i] * 32767 * gain)), round half to even. */
+int st2_pcm16(const float* wav, long long n, float gain, short* out, void* stream);
 
 /* ------------------------------------------------------------------ reference-style path
  * compute_style (Demo/Inference_LibriTTS.ipynb cell 5): wave -> log-mel -> StyleEncoder x2 (models.py:139-164).

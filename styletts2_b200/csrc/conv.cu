@@ -212,14 +212,11 @@ static int conv_launch(const st2_conv_args& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------
 // weight preparation
-__global__ void weight_norm_fold_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w,
-                                        int rows, int cols) {
-  const int r = blockIdx.x;
-  const float* vr = v + (long long)r * cols;
-  // two-pass, fp64 accumulation: folded once at load, accuracy over speed
+// sum of squares of one row, fp64 accumulation, fixed reduction order (shared by the fold and the row-norm kernel so that
+// a weight exported folded and re-imported as (v = w, g = ||w||) folds back to exactly w: scale == 1.0f)
+__device__ __forceinline__ double row_sumsq_block(const float* __restrict__ vr, int cols, double* red) {
   double ss = 0.0;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) ss += (double)vr[c] * (double)vr[c];
-  __shared__ double red[32];
   ss = warp_sum_d(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
   __syncthreads();
@@ -229,6 +226,23 @@ __global__ void weight_norm_fold_kernel(const float* __restrict__ v, const float
     if (threadIdx.x == 0) red[0] = t;
   }
   __syncthreads();
+  return red[0];
+}
+
+__global__ void row_norm_kernel(const float* __restrict__ v, float* __restrict__ out, int rows, int cols) {
+  __shared__ double red[32];
+  const int r = blockIdx.x;
+  const double ss = row_sumsq_block(v + (long long)r * cols, cols, red);
+  if (threadIdx.x == 0) out[r] = (float)sqrt(ss);
+}
+
+__global__ void weight_norm_fold_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w,
+                                        int rows, int cols) {
+  const int r = blockIdx.x;
+  const float* vr = v + (long long)r * cols;
+  // two-pass, fp64 accumulation: folded once at load, accuracy over speed
+  __shared__ double red[32];
+  row_sumsq_block(vr, cols, red);
   const float scale = g[r] / (float)sqrt(red[0]);  // torch: v * (g / norm)
   for (int c = threadIdx.x; c < cols; c += blockDim.x) w[(long long)r * cols + c] = vr[c] * scale;
 }
@@ -435,6 +449,14 @@ int st2_conv_transpose1d(const st2_conv_args* a0, const float* wp, int K, int S,
     if (rc) return rc;
   }
   ST2_CHECK_LAUNCH("st2_conv_transpose1d");
+  return 0;
+}
+
+int st2_row_norm(const float* v, float* out, int rows, int cols, void* stream) {
+  ST2_REQUIRE(v && out && rows > 0 && cols > 0, "st2_row_norm", "bad args");
+  row_norm_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(v, out, rows, cols);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_row_norm");
   return 0;
 }
 

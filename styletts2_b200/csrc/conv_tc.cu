@@ -89,6 +89,10 @@ constexpr int B_WFULL = 0, B_WEMPTY = 6, B_AFULL = 12, B_AEMPTY = 14, B_TFULL = 
 
 // Optional per-role cycle trace of CTA 0 (debug/profiling aid; null in production).
 __device__ long long* g_trace = nullptr;
+// Timing-experiment switches (tools/tc_bench.py; results are WRONG when any is set; 0 in production):
+//   1 = FAST recipe issues its second MMA as kind::f16 (cost of switching MMA kinds), 2 = epilogue without global traffic,
+//   4 = stagers skip the conversion (stale operands), 8 = no MMAs issued (commits only)
+__device__ int g_dbg = 0;
 constexpr int TRACE_TILES = 16, TRACE_K = 8;  // [role 4][tile 16][8 counters]
 __device__ __forceinline__ void trace_put(int role, int it, int k, long long v) {
   if (g_trace && blockIdx.x == 0 && it < TRACE_TILES) g_trace[(role * TRACE_TILES + it) * TRACE_K + k] = v;
@@ -272,6 +276,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     if (lane == 0) {
       const uint32_t idesc = make_idesc();
       const uint32_t lbo_a = TM * 16, lbo_b = (uint32_t)RWP * 16;
+      const int dbg = g_dbg;
       int ws = 0, wph = 0, as = 0, aph = 0;
       auto wait_pumping = [&](uint32_t bar, uint32_t parity) -> long long { return mbar_wait_timed(bar, parity); };
       int it = 0;
@@ -297,10 +302,13 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
             {
               const uint64_t da0 = make_desc(w0, lbo_a, 128), da1 = make_desc(w1, lbo_a, 128);
               const uint64_t db0 = make_desc(act0 + row_off, lbo_b, 128), db1 = make_desc(act1 + row_off, lbo_b, 128);
-              tc_mma(d0, da0, db0, idesc, first ? 0u : 1u);
-              if (MODE == MODE_FAST) {
-                tc_mma_f8(d0, da1, db1, idesc, 1u);              // both corrections in one e4m3 K=32 MMA
+              if (dbg & 8) {
+              } else if (MODE == MODE_FAST) {
+                tc_mma(d0, da0, db0, idesc, first ? 0u : 1u);
+                if (dbg & 1) tc_mma(d0, da1, db1, idesc, 1u);
+                else tc_mma_f8(d0, da1, db1, idesc, 1u);         // both corrections in one e4m3 K=32 MMA
               } else {
+                tc_mma(d0, da0, db0, idesc, first ? 0u : 1u);
                 tc_mma(d1, da0, db1, idesc, (MODE == MODE_ACC && first) ? 0u : 1u);
                 tc_mma(d1, da1, db0, idesc, 1u);
               }
@@ -396,6 +404,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     // conversion mapping: warp parity -> K chunk, (warp / 2, lane) -> 160 rows per pass: every shared-memory access of
     // a warp touches consecutive words / consecutive 16-byte rows
     const int sw = warp - 2;
+    const int dbg_st = g_dbg;
     const int kc = sw & 1, rg = (sw >> 1) * 32 + lane;
     constexpr int NRC = (RW_MAX + 159) / 160;
     const float xs_ = X_SCALE;
@@ -443,7 +452,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
 #pragma unroll
       for (int i = 0; i < NRC; ++i) {
         const int r = rg + 160 * i;
-        if (r < RW) {
+        if (r < RW && !(dbg_st & 4)) {
           const int gt = c_g0 + r;
           const bool inb = (gt >= 0) && (gt < Lin_);
           float xv[8];
@@ -470,6 +479,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     const int ytst_ = a.y_tstride, ytoff_ = a.y_toffset, rshift_ = a.res_shift;
     const float out_div_ = a.out_div, acc_div_ = a.accum_div;
     const bool has_stats = a.stats != nullptr;
+    const bool dbg_noio = (g_dbg & 2) != 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
@@ -496,7 +506,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           const bool okc = (c0 + lane) < ncols;
           const float* rp0 = rb ? rb + ((tcol * ytst_ + ytoff_) >> rshift_) : nullptr;
 #pragma unroll
-          for (int r = 0; r < 32; ++r) rv[r] = (rb && okc && r < rmax) ? __ldg(rp0 + (long long)r * res_len_) : 0.f;
+          for (int r = 0; r < 32; ++r) rv[r] = (rb && okc && r < rmax && !dbg_noio) ? __ldg(rp0 + (long long)r * res_len_) : 0.f;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + c0);
         tmem_ld32(taddr, v);
@@ -513,7 +523,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
         for (int j = 0; j < 32; ++j) v[j] *= D_UNSCALE;
         const long long q1 = clock64();
         tr_ld += q1 - q0;
-        if (c0 >= ncols || rmax <= 0) continue;
+        if (c0 >= ncols || rmax <= 0 || dbg_noio) continue;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<float4*>(&T[lane * TPITCH + 4 * q]) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -766,6 +776,12 @@ int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int mode, int max_cta
   ST2_REQUIRE(!a->stats || a->stats_nparts >= a->stats_part_offset + 2 * n_tq, "st2_conv1d_tc", "stats buffer too small (2 partials per 256-column tile)");
   tc::launch_tc(*a, wtc, mode, max_ctas, (cudaStream_t)stream);
   ST2_CHECK_LAUNCH("st2_conv1d_tc");
+  return 0;
+}
+
+int st2_debug_set_flags(int flags) {
+  cudaError_t e = cudaMemcpyToSymbol(tc::g_dbg, &flags, sizeof(flags));
+  if (e != cudaSuccess) { set_error("st2_debug_set_flags", e); return (int)e; }
   return 0;
 }
 

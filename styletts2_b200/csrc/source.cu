@@ -254,7 +254,36 @@ __global__ void __launch_bounds__(320) istft20_kernel(const float* __restrict__ 
 
 using namespace st2;
 
+// fp32 waveform -> 16-bit PCM (row f4: the wire format after the path): round-half-even of x * 32767 * gain, saturated.
+// Four samples per thread (128-bit load, 64-bit store) when the row is aligned.
+__global__ void pcm16_kernel(const float* __restrict__ x, long long n, float gain, short* __restrict__ out) {
+  const long long i4 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  auto q = [gain](float v) -> short {
+    float r = rintf(v * gain);
+    r = fminf(fmaxf(r, -32768.f), 32767.f);
+    return (short)(int)r;
+  };
+  if (i4 + 3 < n && ((reinterpret_cast<size_t>(x) & 15) == 0) && ((reinterpret_cast<size_t>(out) & 7) == 0)) {
+    const float4 v = *reinterpret_cast<const float4*>(x + i4);
+    short4 o;
+    o.x = q(v.x); o.y = q(v.y); o.z = q(v.z); o.w = q(v.w);
+    *reinterpret_cast<short4*>(out + i4) = o;
+  } else {
+    for (long long i = i4; i < n && i < i4 + 4; ++i) out[i] = q(x[i]);
+  }
+}
+
 extern "C" {
+
+int st2_pcm16(const float* wav, long long n, float gain, short* out, void* stream) {
+  ST2_REQUIRE(wav && out && n > 0, "st2_pcm16", "bad args");
+  const long long threads = (n + 3) / 4;
+  pcm16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wav, n, 32767.0f * gain, out);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_pcm16");
+  return 0;
+}
 
 int st2_rng_advance(unsigned long long* epoch, void* stream) {
   ST2_REQUIRE(epoch, "st2_rng_advance", "bad args");

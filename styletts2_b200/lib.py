@@ -61,6 +61,7 @@ SIGNATURES = {
     "st2_abi_version": [],
     "st2_launch_count": [],
     "st2_weight_norm_fold": [_vp, _vp, _vp, _i, _i, _vp],
+    "st2_row_norm": [_vp, _vp, _i, _i, _vp],
     "st2_conv_weight_layout": [_vp, _vp, _i, _i, _i, _vp],
     "st2_convT_weight_layout": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
     "st2_conv1d": [C.POINTER(ConvArgs), _vp],
@@ -70,6 +71,7 @@ SIGNATURES = {
     "st2_conv_tc_supported": [_i, _i, _i, _i, _i],
     "st2_conv1d_tc": [C.POINTER(ConvArgs), _vp, _i, _i, _vp],
     "st2_debug_set_trace": [_vp],
+    "st2_debug_set_flags": [_i],
     "st2_convT_tc_weight_bytes": [_i, _i, _i, _i],
     "st2_convT_tc_weight_layout": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "st2_conv_transpose1d_tc": [C.POINTER(ConvArgs), _vp, _i, _i, _i, _i, _i, _vp],
@@ -116,6 +118,7 @@ SIGNATURES = {
     "st2_logmel": [_vp, _i, _i, _i, _f, _f, _f, _vp, _vp],
     "st2_stft20": [_vp, _i, _i, _vp, _vp],
     "st2_istft20_expsin": [_vp, _i, _i, _vp, _vp],
+    "st2_pcm16": [_vp, _ll, _f, _vp, _vp],
 }
 _RESTYPES = {"st2_last_error": C.c_char_p, "st2_launch_count": C.c_longlong, "st2_conv_tc_weight_bytes": C.c_longlong,
              "st2_convT_tc_weight_bytes": C.c_longlong, "st2_linear_tc_weight_bytes": C.c_longlong,

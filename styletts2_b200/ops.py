@@ -39,6 +39,15 @@ def fold_weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     return w.view_as(v)
 
 
+def row_norm(v: torch.Tensor) -> torch.Tensor:
+    """||v[r,:]||_2 per leading-dim row with the fold kernel's reduction -> [rows]"""
+    rows = v.shape[0]
+    v2 = v.detach().contiguous().view(rows, -1)
+    out = torch.empty(rows, device=v.device, dtype=f32)
+    L.call("st2_row_norm", ptr(v2), ptr(out), rows, v2.shape[1], stream_ptr())
+    return out
+
+
 def conv_weight_layout(w: torch.Tensor) -> torch.Tensor:
     """[Cout,Cin,K] -> [Cin,K,Cout]"""
     w = w.detach().contiguous()
@@ -521,6 +530,15 @@ def istft20_expsin(x):
     with _prof(f"istft20 F{Fr} B{B}", 0.0, 4.0 * B * (22 * Fr + 5 * (Fr - 1))):
         L.call("st2_istft20_expsin", ptr(x), B, Fr, ptr(wav), stream_ptr())
     return wav
+
+
+def pcm16(wav: torch.Tensor, gain: float = 1.0) -> torch.Tensor:
+    """fp32 waveform (any shape) -> int16 PCM on the device: saturate(rint(x * 32767 * gain))"""
+    wav = wav.contiguous()
+    out = torch.empty(wav.shape, dtype=torch.int16, device=wav.device)
+    with _prof(f"pcm16 n{wav.numel()}", 0.0, 6.0 * wav.numel()):
+        L.call("st2_pcm16", ptr(wav), wav.numel(), float(gain), ptr(out), stream_ptr())
+    return out
 
 
 def kdiff_combine(out, out_masked, scale_):

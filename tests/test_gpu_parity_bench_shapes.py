@@ -69,7 +69,7 @@ def test_bench_shape_parity(name):
     hist = torch.histc(torch.log10(guard.clamp_min(1e-12)).float(), bins=8, min=-8, max=0).tolist()
     dur_err = float((out["dur_f"].cpu().double() - dur_f).abs().max())
     record("bench_shape_durations_" + name, tokens=B * N, mismatches=nbad, min_guard=float(guard.min()), duration_sum_maxabs_err=dur_err,
-           guard_log10_hist_1e-8_to_1=str([int(h) for h in hist]), s_pred_maxabs=maxdiff(out["s_pred"], front["s_pred"]),
+           guard_log10_hist_m8_to_0=str([int(h) for h in hist]), s_pred_maxabs=maxdiff(out["s_pred"], front["s_pred"]),
            logits_maxabs=maxdiff(out["logits"], front["logits"]))
     assert nbad == 0, f"{nbad} of {B * N} integer durations differ (min guard band {float(guard.min()):.2e}, sum error {dur_err:.2e})"
 
