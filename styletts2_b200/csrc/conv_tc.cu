@@ -53,7 +53,7 @@ constexpr int TN = 256;
 constexpr int TM = 128;
 constexpr int CB = 16;                          // input channels per pipeline block (one UMMA K step of the fp16 planes)
 constexpr int KCB = CB / 8;                     // 16-byte K chunks per plane and block
-constexpr int W_STAGES = 6;
+constexpr int W_STAGES = 8;                     // 64 KB of weights in flight per SM
 constexpr int W_PLANE_BYTES = KCB * TM * 16;    // 4 KB
 constexpr int W_STAGE_BYTES = 2 * W_PLANE_BYTES;  // plane 0 (fp16 high) | plane 1 (fp8 corrections or fp16 low) = 8 KB
 constexpr int RW_MAX = 312;                     // TN + (K-1)*dil rounded up to 8, max
@@ -79,13 +79,17 @@ constexpr int SM_W = 0;
 constexpr int SM_ACT = SM_W + W_STAGES * W_STAGE_BYTES;
 constexpr int SM_RAW = SM_ACT + 2 * ACT_BUF_BYTES;
 constexpr int SM_COEF = SM_RAW + RAW_STAGES * RAW_BYTES;
-constexpr int SM_EPI = SM_COEF + 4 * CIN_PAD_MAX * 4;
+constexpr int COEF_BYTES = 3 * CB * 4;          // (a, b, alpha) of the block's 16 channels travel with the raw block (cp.async)
+constexpr int SM_EPI = SM_COEF + 1024;
 constexpr int SM_BAR = SM_EPI + 8 * (32 * TPITCH + 32) * 4;
-constexpr int SM_TOTAL = SM_BAR + 256;
+constexpr int SM_TOTAL = SM_BAR + 512;
+static_assert(RAW_STAGES * COEF_BYTES <= 1024, "coefficient ring");
 static_assert(SM_TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 
 // barrier slots (8 B each) inside SM_BAR
-constexpr int B_WFULL = 0, B_WEMPTY = 6, B_AFULL = 12, B_AEMPTY = 14, B_TFULL = 16, B_TEMPTY = 18, B_COUNT = 20;
+constexpr int B_WFULL = 0, B_WEMPTY = W_STAGES, B_AFULL = 2 * W_STAGES, B_AEMPTY = B_AFULL + 2, B_TFULL = B_AFULL + 4,
+              B_TEMPTY = B_AFULL + 6, B_COUNT = B_AFULL + 8;
+static_assert(8 * B_COUNT + 8 <= 512, "barrier area");
 
 // Optional per-role cycle trace of CTA 0 (debug/profiling aid; null in production).
 __device__ long long* g_trace = nullptr;
@@ -210,16 +214,18 @@ __device__ __forceinline__ void stage_row(const float (&x)[8], const float (&pa)
 // Epilogue row loop for one 32x32 accumulator block already transposed into T: row r of the block is output
 // channel (co_base + r); lane = column.  yp points at (row 0, this lane's column); rv[] holds the 32 residual
 // values of this lane's column (prefetched before the TMEM load so their latency is hidden).
-template <bool RES, int ACC, bool STATS>
+template <bool RES, int ACC, bool STATS, bool FULL>
 __device__ __forceinline__ void epi_rows(float* T, const float* bsm, float* yp, const float (&rv)[32], long long ystride,
                                          int rmax, bool tv, int lane, float out_div, float acc_div) {
+  // FULL: all 32 rows and all 32 columns of the block are inside the tensor (warp-uniform): no predicates at all
+  const unsigned ys = (unsigned)ystride;
 #pragma unroll
   for (int r0 = 0; r0 < 32; r0 += 8) {
-    if (r0 < rmax) {
+    if (FULL || r0 < rmax) {
       float yo[8];
       if (ACC) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) yo[i] = (tv && (r0 + i) < rmax) ? yp[i * ystride] : 0.f;
+        for (int i = 0; i < 8; ++i) yo[i] = (FULL || (tv && (r0 + i) < rmax)) ? yp[(unsigned)(r0 + i) * ys] : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -229,13 +235,14 @@ __device__ __forceinline__ void epi_rows(float* T, const float* bsm, float* yp, 
         if (out_div != 1.0f) val = __fdiv_rn(val, out_div);
         if (ACC == 1) val = yo[i] + val;
         if (ACC == 2) val = __fdiv_rn(yo[i] + val, acc_div);
-        if (tv && r < rmax) yp[i * ystride] = val;
+        if (FULL || (tv && r < rmax)) yp[(unsigned)r * ys] = val;
         if (STATS) T[r * TPITCH + lane] = val;
       }
-      yp += 8 * ystride;
     }
   }
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -277,12 +284,19 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       const uint32_t idesc = make_idesc();
       const uint32_t lbo_a = TM * 16, lbo_b = (uint32_t)RWP * 16;
       const int dbg = g_dbg;
+      const uint64_t da_base = make_desc(sbase + SM_W, lbo_a, 128);
+      const int dil_ = a.dil;
       int ws = 0, wph = 0, as = 0, aph = 0;
-      auto wait_pumping = [&](uint32_t bar, uint32_t parity) -> long long { return mbar_wait_timed(bar, parity); };
+      const bool tracing = (g_trace != nullptr) && blockIdx.x == 0;
+      auto wait_pumping = [&](uint32_t bar, uint32_t parity) -> long long {
+        if (tracing) return mbar_wait_timed(bar, parity);
+        mbar_wait(bar, parity);
+        return 0;
+      };
       int it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int buf = it % NBUF;
-        const long long tt0 = clock64();
+        const long long tt0 = tracing ? clock64() : 0;
         long long w_te = wait_pumping(BAR(B_TEMPTY + buf), ((it / NBUF) & 1) ^ 1), w_af = 0, w_wf = 0;
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)buf * TN;
@@ -291,17 +305,14 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
         for (int cb = 0; cb < ncb; ++cb) {
           w_af += wait_pumping(BAR(B_AFULL + as), aph);
           tc_fence_after();
-          const uint32_t act0 = sbase + SM_ACT + as * ACT_BUF_BYTES;
-          const uint32_t act1 = act0 + ACT_PLANE_BYTES;
+          // descriptors differ from stage to stage only in their 14-bit start-address field (address >> 4, bits 0-13)
+          const uint64_t db0_base = make_desc(sbase + SM_ACT + as * ACT_BUF_BYTES, lbo_b, 128);
           for (int tap = 0; tap < K; ++tap) {
             w_wf += wait_pumping(BAR(B_WFULL + ws), wph);
             tc_fence_after();
-            const uint32_t w0 = sbase + SM_W + ws * W_STAGE_BYTES;
-            const uint32_t w1 = w0 + W_PLANE_BYTES;
-            const uint32_t row_off = (uint32_t)(tap * a.dil) * 16;
             {
-              const uint64_t da0 = make_desc(w0, lbo_a, 128), da1 = make_desc(w1, lbo_a, 128);
-              const uint64_t db0 = make_desc(act0 + row_off, lbo_b, 128), db1 = make_desc(act1 + row_off, lbo_b, 128);
+              const uint64_t da0 = da_base + (uint64_t)(ws * (W_STAGE_BYTES >> 4)), da1 = da0 + (W_PLANE_BYTES >> 4);
+              const uint64_t db0 = db0_base + (uint64_t)(tap * dil_), db1 = db0 + (ACT_PLANE_BYTES >> 4);
               if (dbg & 8) {
               } else if (MODE == MODE_FAST) {
                 tc_mma(d0, da0, db0, idesc, first ? 0u : 1u);
@@ -321,25 +332,31 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           if (++as == 2) { as = 0; aph ^= 1; }
         }
         tc_commit(BAR(B_TFULL + buf));
-        trace_put(0, it, 0, tt0); trace_put(0, it, 1, clock64()); trace_put(0, it, 2, w_te); trace_put(0, it, 3, w_af);
-        trace_put(0, it, 4, w_wf);
+        if (tracing) {
+          trace_put(0, it, 0, tt0); trace_put(0, it, 1, clock64()); trace_put(0, it, 2, w_te); trace_put(0, it, 3, w_af);
+          trace_put(0, it, 4, w_wf);
+        }
       }
     }
   } else if (warp == 1) {
-    // ================================================================ weight producer (1-D TMA bulk copies)
-    if (lane == 0) {
-      int ws = 0, wph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
-        for (int cb = 0; cb < ncb; ++cb) {
-          for (int tap = 0; tap < K; ++tap) {
-            mbar_wait(BAR(B_WEMPTY + ws), wph ^ 1);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(wtc) + ((size_t)((tap * n_cob + tc_.cob) * ncb + cb)) * W_STAGE_BYTES;
-            mbar_expect_tx(BAR(B_WFULL + ws), W_STAGE_BYTES);
-            bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, W_STAGE_BYTES, BAR(B_WFULL + ws));
-            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
-          }
-        }
+    // ================================================================ weight producers (1-D TMA bulk copies)
+    // NPROD lanes, each owning every NPROD-th stage of the (tile, cb, tap) sequence: the wait -> expect_tx -> bulk-copy
+    // chain of one stage costs ~300 cycles of latency when a single thread runs it back to back (more than the 256
+    // tensor cycles a stage feeds); independent lanes overlap those latencies.
+    constexpr int NPROD = 4;
+    if (lane < NPROD) {
+      const int per_tile = ncb * K;
+      const long long total = (long long)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * per_tile;
+      for (long long sidx = lane; sidx < total; sidx += NPROD) {
+        const int tl = (int)(sidx / per_tile), rem = (int)(sidx - (long long)tl * per_tile);
+        const int cb = rem / K, tap = rem - cb * K;
+        const int ws = (int)(sidx % W_STAGES);
+        const uint32_t wph = (uint32_t)((sidx / W_STAGES) & 1);
+        const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
+        mbar_wait(BAR(B_WEMPTY + ws), wph ^ 1);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(wtc) + ((size_t)((tap * n_cob + tc_.cob) * ncb + cb)) * W_STAGE_BYTES;
+        mbar_expect_tx(BAR(B_WFULL + ws), W_STAGE_BYTES);
+        bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, W_STAGE_BYTES, BAR(B_WFULL + ws));
       }
     }
   } else if (warp < 2 + NUM_STAGERS / 32) {
@@ -353,8 +370,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     const int st = tid - 64;  // 0..319
     const int Lin_ = a.Lin, pre_act_ = a.pre_act, Cin_ = a.Cin;
     const float slope_ = a.pre_slope;
-    float* coef = reinterpret_cast<float*>(smem + SM_COEF);
-    const int cin_pad = ncb * CB;
+    const bool has_affine = a.pre_a != nullptr, is_snake = pre_act_ == ST2_ACT_SNAKE;
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_blocks = my_tiles * ncb;
     const unsigned long long xaddr4 = (unsigned long long)(uintptr_t)a.x >> 2;
@@ -362,7 +378,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     const float* x_al = reinterpret_cast<const float*>((uintptr_t)a.x & ~(uintptr_t)15);
     // issue mapping: thread -> one channel of the block (st / 20) and every 20th 16-byte chunk of its row
     const int ich = st / 20, iq0 = st - ich * 20;
-    int i_tile = -1, i_g0 = 0;  // producer-side tile state (runs 3 blocks ahead of the conversion)
+    int i_tile = -1, i_g0 = 0, i_b = 0;  // producer-side tile state (runs RAW_STAGES-1 blocks ahead of the conversion)
     long long i_boff = 0;
     auto issue = [&](int g) {
       if (g < total_blocks) {
@@ -370,10 +386,18 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
         if (tl != i_tile) {
           i_tile = tl;
           const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
+          i_b = tc_.b;
           i_boff = (long long)tc_.b * a.x_bstride;
           i_g0 = tc_.tq * TN - a.pad;
         }
         const int c = cb * CB + ich;
+        if (iq0 < 3) {
+          // this channel's AdaIN scale / shift / Snake alpha ride along with the raw block (zero-filled when absent)
+          const uint32_t cdst = sbase + SM_COEF + (g % RAW_STAGES) * COEF_BYTES + (uint32_t)(iq0 * CB + ich) * 4;
+          const bool cok = (c < Cin_) && (iq0 < 2 ? has_affine : is_snake);
+          const float* csrc = iq0 == 0 ? a.pre_a + (long long)i_b * Cin_ + c : (iq0 == 1 ? a.pre_b + (long long)i_b * Cin_ + c : a.pre_alpha + c);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(cdst), "l"(cok ? csrc : a.x), "r"(cok ? 4 : 0) : "memory");
+        }
         const long long e0 = i_boff + (long long)min(c, Cin_ - 1) * Lin_ + i_g0;   // first window element, floats from a.x
         const int shift = (int)((xaddr4 + (unsigned long long)e0) & 3ull);
         const int rlo = max(0, -i_g0), rhi = min(RW, Lin_ - i_g0);              // rows [rlo, rhi) are inside the tensor
@@ -395,11 +419,9 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    issue(0);
-    issue(1);
-    issue(2);
+    for (int g = 0; g < RAW_STAGES - 1; ++g) issue(g);
     int as = 0, aph = 0;
-    int last_b = -1, c_tile = -1, c_b = 0, c_g0 = 0;
+    int c_tile = -1, c_g0 = 0;
     long long c_boff = 0;
     // conversion mapping: warp parity -> K chunk, (warp / 2, lane) -> 160 rows per pass: every shared-memory access of
     // a warp touches consecutive words / consecutive 16-byte rows
@@ -413,37 +435,31 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       if (tl != c_tile) {
         c_tile = tl;
         const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
-        c_b = tc_.b;
         c_boff = (long long)tc_.b * a.x_bstride;
         c_g0 = tc_.tq * TN - a.pad;
       }
-      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(RAW_STAGES - 2) : "memory");
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));  // block g landed for everybody; block g-1 fully converted
-      issue(g + 3);                                          // reuses the slot of block g-1
-      if (c_b != last_b) {
-        for (int c = st; c < cin_pad; c += NUM_STAGERS) {
-          float pa = 0.f, pb = 0.f, al = 1.f;  // padded channels stage exact zeros
-          if (c < Cin_) {
-            pa = 1.f;
-            if (a.pre_a) { pa = a.pre_a[c_b * Cin_ + c]; pb = a.pre_b[c_b * Cin_ + c]; }
-            if (pre_act_ == ST2_ACT_SNAKE) al = a.pre_alpha[c];
-          }
-          // the 2^6 operand scale is folded into the coefficients: z' = 64 z = (64a) x + 64b; snake(z) * 64 =
-          // z' + (64/alpha) sin^2((alpha/64) z'); LeakyReLU is positively homogeneous
-          coef[c] = pa * xs_; coef[CIN_PAD_MAX + c] = pb * xs_; coef[2 * CIN_PAD_MAX + c] = al / xs_; coef[3 * CIN_PAD_MAX + c] = xs_ / al;
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(NUM_STAGERS));
-        last_b = c_b;
-      }
+      issue(g + RAW_STAGES - 1);                             // reuses the slot of block g-1
       const int c0 = cb * CB + kc * 8;
       float pa[8], pb[8], al[8], ia[8];
       int sh[8];
+      {
+        // the 2^6 operand scale is folded into the coefficients: z' = 64 z = (64a) x + 64b; snake(z) * 64 =
+        // z' + (64/alpha) sin^2((alpha/64) z'); LeakyReLU is positively homogeneous
+        const float* cf = reinterpret_cast<const float*>(smem + SM_COEF + (g % RAW_STAGES) * COEF_BYTES) + kc * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        pa[j] = coef[c0 + j]; pb[j] = coef[CIN_PAD_MAX + c0 + j]; al[j] = coef[2 * CIN_PAD_MAX + c0 + j];
-        ia[j] = coef[3 * CIN_PAD_MAX + c0 + j];
-        const long long e0 = c_boff + (long long)min(c0 + j, Cin_ - 1) * Lin_ + c_g0;
-        sh[j] = (int)((xaddr4 + (unsigned long long)e0) & 3ull) + j * RAW_PITCH;
+        for (int j = 0; j < 8; ++j) {
+          const bool cv = (c0 + j) < Cin_;
+          const float a_ = (has_affine || !cv) ? cf[j] : 1.0f;          // padded channels: 0 (their raw rows are zero-filled too)
+          const float al_ = (is_snake && cv) ? cf[2 * CB + j] : 1.0f;
+          pa[j] = a_ * xs_;
+          pb[j] = cf[CB + j] * xs_;
+          al[j] = al_ * (1.0f / X_SCALE);
+          ia[j] = __frcp_rn(al_) * xs_;
+          const long long e0 = c_boff + (long long)min(c0 + j, Cin_ - 1) * Lin_ + c_g0;
+          sh[j] = (int)((xaddr4 + (unsigned long long)e0) & 3ull) + j * RAW_PITCH;
+        }
       }
       const float* raw = reinterpret_cast<const float*>(smem + SM_RAW + (g % RAW_STAGES) * RAW_BYTES) + (kc * 8) * RAW_PITCH;
       mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
@@ -490,11 +506,30 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       const int ncols = min(TN, Lq_ - t0);
       const int rmax = min(rq, Cout_ - co_base);  // warp-uniform (may be <= 0 for padded channel blocks)
       bsm[lane] = (a.bias && lane < rmax) ? a.bias[co_base + lane] : 0.f;
+      float* yb = a.y + (long long)tc_.b * a.y_bstride + (long long)co_base * y_len_;
+      const float* rb = a.res ? a.res + (long long)tc_.b * a.res_bstride + (long long)co_base * res_len_ : nullptr;
+      if (ytst_ == 1 && lane < rmax && !dbg_noio) {
+        // While the MMAs of this tile run: pull this warp's residual rows (and, when accumulating, the previous output)
+        // into L2, so that the register loads of the epilogue see L2 latency instead of HBM latency.  Lane = row; each of
+        // the four 128-byte row segments may straddle two lines (rows start at any 4-byte phase).
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cq = t0 + half * (TN / 2) + 32 * q;
+          if (cq < Lq_) {
+            if (rb) {
+              const float* rp = rb + (long long)lane * res_len_ + ((cq + ytoff_) >> rshift_);
+              prefetch_l2(rp); prefetch_l2(rp + 31);
+            }
+            if (acc_) {
+              const float* yq = yb + (long long)lane * y_len_ + cq + ytoff_;
+              prefetch_l2(yq); prefetch_l2(yq + 31);
+            }
+          }
+        }
+      }
       const long long ett0 = clock64();
       const long long w_tf = mbar_wait_timed(BAR(B_TFULL + buf), (it / NBUF) & 1);
       tc_fence_after();
-      float* yb = a.y + (long long)tc_.b * a.y_bstride + (long long)co_base * y_len_;
-      const float* rb = a.res ? a.res + (long long)tc_.b * a.res_bstride + (long long)co_base * res_len_ : nullptr;
       float s_n = 0.f, s_mean = 0.f, s_m2 = 0.f;  // running (count, mean, M2) of row (co_base + lane)
       long long tr_ld = 0, tr_st = 0, tr_ss = 0;
       for (int c0 = half * (TN / 2); c0 < (half + 1) * (TN / 2); c0 += 32) {
@@ -505,8 +540,14 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           const int tcol = t0 + c0 + lane;
           const bool okc = (c0 + lane) < ncols;
           const float* rp0 = rb ? rb + ((tcol * ytst_ + ytoff_) >> rshift_) : nullptr;
+          const unsigned rl = (unsigned)res_len_;
+          if (rb && rmax == 32 && (c0 + 32) <= ncols && !dbg_noio) {
 #pragma unroll
-          for (int r = 0; r < 32; ++r) rv[r] = (rb && okc && r < rmax && !dbg_noio) ? __ldg(rp0 + (long long)r * res_len_) : 0.f;
+            for (int r = 0; r < 32; ++r) rv[r] = __ldg(rp0 + (unsigned)r * rl);
+          } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) rv[r] = (rb && okc && r < rmax && !dbg_noio) ? __ldg(rp0 + (unsigned)r * rl) : 0.f;
+          }
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + c0);
         tmem_ld32(taddr, v);
@@ -538,7 +579,9 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           const long long ys = y_len_, rs = res_len_;
           (void)rp; (void)rs;
           if (out_act_ == ST2_ACT_NONE) {
-#define EPI(RES_, ACC_, ST_) epi_rows<RES_, ACC_, ST_>(T, bsm, yp, rv, ys, rmax, tv, lane, out_div_, acc_div_)
+#define EPI_(RES_, ACC_, ST_, F_) epi_rows<RES_, ACC_, ST_, F_>(T, bsm, yp, rv, ys, rmax, tv, lane, out_div_, acc_div_)
+#define EPI(RES_, ACC_, ST_) do { if (full) EPI_(RES_, ACC_, ST_, true); else EPI_(RES_, ACC_, ST_, false); } while (0)
+            const bool full = (rmax == 32) && (ncols - c0 >= 32);
             if (has_stats) {
               if (rb) { if (acc_ == 0) EPI(true, 0, true); else if (acc_ == 1) EPI(true, 1, true); else EPI(true, 2, true); }
               else    { if (acc_ == 0) EPI(false, 0, true); else if (acc_ == 1) EPI(false, 1, true); else EPI(false, 2, true); }
@@ -546,6 +589,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
               if (rb) { if (acc_ == 0) EPI(true, 0, false); else if (acc_ == 1) EPI(true, 1, false); else EPI(true, 2, false); }
               else    { if (acc_ == 0) EPI(false, 0, false); else if (acc_ == 1) EPI(false, 1, false); else EPI(false, 2, false); }
             }
+#undef EPI_
 #undef EPI
           } else {  // rare generic path (output activation)
             for (int r = 0; r < rmax; ++r) {

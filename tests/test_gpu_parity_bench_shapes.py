@@ -5,8 +5,9 @@
 The engine runs the WHOLE batch exactly as bench.py does (same synthetic inputs, durations pinned to 4 frames per token
 after the duration kernel has run); the CPU oracle runs
   * the text side (text encoder, sampler, duration predictor) on the whole batch: integer durations must be bit-exact on
-    all B*N tokens (4096 / 1024 / 8000), and the distance of every pre-rounding sum to the nearest rounding boundary is
-    recorded (guard-band statistics, SURVEY section 7 hard-part 2);
+    all B*N tokens (4096 / 1024 / 8000) except tokens whose pre-rounding sum is within fp32 noise of a rounding boundary
+    (see the assertion), and the distance of every sum to the nearest boundary is recorded (guard-band statistics,
+    SURVEY section 7 hard-part 2);
   * the full path on TWO utterances of the batch alone (first and last; every op is per-utterance): F0 / N curves and --
     with the oracle's F0/N (and har for iSTFTNet) teacher-forced for those two utterances only -- the waveform <= 1e-3.
 Tile tails (L = 61441, 240001), Cin = 1090, the 15-cluster LSTM grouping at B = 32 and 240 stats partials per row are
@@ -71,7 +72,16 @@ def test_bench_shape_parity(name):
     record("bench_shape_durations_" + name, tokens=B * N, mismatches=nbad, min_guard=float(guard.min()), duration_sum_maxabs_err=dur_err,
            guard_log10_hist_m8_to_0=str([int(h) for h in hist]), s_pred_maxabs=maxdiff(out["s_pred"], front["s_pred"]),
            logits_maxabs=maxdiff(out["logits"], front["logits"]))
-    assert nbad == 0, f"{nbad} of {B * N} integer durations differ (min guard band {float(guard.min()):.2e}, sum error {dur_err:.2e})"
+    # Bit-exact everywhere EXCEPT where the reference's own pre-rounding sum lies closer to a rounding boundary than fp32
+    # arithmetic can resolve: the sums (~25, 50 sigmoid terms behind four LSTMs) agree with the oracle's to ~2e-5 (8e-7
+    # relative, the level any two fp32 evaluation orders differ by), and among 8000 tokens one or two land within that
+    # distance of x.5 (C4: one token at 1.9e-6).  Such a token may round either way; nothing else may differ.
+    assert dur_err < 1e-4, dur_err
+    bad = (pd != pd_ref)
+    assert nbad <= 2 and bool((guard[bad] <= 4 * dur_err).all()), \
+        f"{nbad} of {B * N} integer durations differ; guard bands {guard[bad].tolist()}, sum error {dur_err:.2e}"
+    if nbad:
+        assert int((pd - pd_ref).abs().max()) == 1
 
     # ---- 2. full path on two utterances alone
     refs = {}
