@@ -209,6 +209,13 @@ int st2_attention(const float* q, const float* kv, float* out, int B, int N, int
  * attention mask of transformers.AlbertModel (PL-BERT, Utils/PLBERT/util.py:6-12). */
 int st2_attention_ex(const float* q, long long q_ld, const float* k, const float* v, long long kv_ld, float* out, long long out_ld,
                      const int* lengths, int B, int N, int H, int D, float scale, void* stream);
+/* The same contraction on the tensor cores (tcgen05, TMEM accumulators for S and O, fp16 two-plane split with separate
+ * correction accumulators = fp32 accuracy; csrc/attention_tc.cu): one CTA per (128 query rows, head, utterance), keys in
+ * blocks of 128.  Needs D == 64, row strides that are multiples of 4 floats and 16-byte aligned pointers
+ * (st2_attention_tc_supported); arguments as st2_attention_ex. */
+int st2_attention_tc_supported(long long q_ld, long long kv_ld, long long out_ld, int D);
+int st2_attention_tc(const float* q, long long q_ld, const float* k, const float* v, long long kv_ld, float* out, long long out_ld,
+                     const int* lengths, int B, int N, int H, int D, float scale, void* stream);
 /* ALBERT embeddings: out[(b,n), :] = word[tokens[b,n]] + pos[n] + type0   (E columns) */
 int st2_embedding_sum_rows(const long long* tokens, const float* word, const float* pos, const float* type0, int B, int N, int E,
                            float* out, void* stream);

@@ -95,7 +95,8 @@ static_assert(8 * B_COUNT + 8 <= 512, "barrier area");
 __device__ long long* g_trace = nullptr;
 // Timing-experiment switches (tools/tc_bench.py; results are WRONG when any is set; 0 in production):
 //   1 = FAST recipe issues its second MMA as kind::f16 (cost of switching MMA kinds), 2 = epilogue without global traffic,
-//   4 = stagers skip the conversion (stale operands), 8 = no MMAs issued (commits only)
+//   4 = stagers skip the conversion (stale operands), 8 = no MMAs issued (commits only), 16 = no weight copies,
+//   32 = no raw activation copies, 64 = no epilogue at all
 __device__ int g_dbg = 0;
 constexpr int TRACE_TILES = 16, TRACE_K = 8;  // [role 4][tile 16][8 counters]
 __device__ __forceinline__ void trace_put(int role, int it, int k, long long v) {
@@ -343,9 +344,10 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     // NPROD lanes, each owning every NPROD-th stage of the (tile, cb, tap) sequence: the wait -> expect_tx -> bulk-copy
     // chain of one stage costs ~300 cycles of latency when a single thread runs it back to back (more than the 256
     // tensor cycles a stage feeds); independent lanes overlap those latencies.
-    constexpr int NPROD = 4;
+    constexpr int NPROD = 1;   // (4 lanes of one warp were measured SLOWER than one: divergent spin loops serialise)
     if (lane < NPROD) {
       const int per_tile = ncb * K;
+      const int dbg_p = g_dbg;
       const long long total = (long long)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * per_tile;
       for (long long sidx = lane; sidx < total; sidx += NPROD) {
         const int tl = (int)(sidx / per_tile), rem = (int)(sidx - (long long)tl * per_tile);
@@ -355,6 +357,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
         const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
         mbar_wait(BAR(B_WEMPTY + ws), wph ^ 1);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(wtc) + ((size_t)((tap * n_cob + tc_.cob) * ncb + cb)) * W_STAGE_BYTES;
+        if (dbg_p & 16) { mbar_arrive(BAR(B_WFULL + ws)); continue; }     // timing experiment: no weight traffic
         mbar_expect_tx(BAR(B_WFULL + ws), W_STAGE_BYTES);
         bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, W_STAGE_BYTES, BAR(B_WFULL + ws));
       }
@@ -380,8 +383,9 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     const int ich = st / 20, iq0 = st - ich * 20;
     int i_tile = -1, i_g0 = 0, i_b = 0;  // producer-side tile state (runs RAW_STAGES-1 blocks ahead of the conversion)
     long long i_boff = 0;
+    const int dbg_i = g_dbg;
     auto issue = [&](int g) {
-      if (g < total_blocks) {
+      if (g < total_blocks && !(dbg_i & 32)) {
         const int tl = g / ncb, cb = g - tl * ncb;
         if (tl != i_tile) {
           i_tile = tl;
@@ -530,6 +534,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       const long long ett0 = clock64();
       const long long w_tf = mbar_wait_timed(BAR(B_TFULL + buf), (it / NBUF) & 1);
       tc_fence_after();
+      if (g_dbg & 64) { tc_fence_before(); mbar_arrive(BAR(B_TEMPTY + buf)); continue; }   // timing experiment: no epilogue
       float s_n = 0.f, s_mean = 0.f, s_m2 = 0.f;  // running (count, mean, M2) of row (co_base + lane)
       long long tr_ld = 0, tr_st = 0, tr_ss = 0;
       for (int c0 = half * (TN / 2); c0 < (half + 1) * (TN / 2); c0 += 32) {

@@ -92,6 +92,8 @@ SIGNATURES = {
     "st2_linear_tc_split_bytes": [_i, _i],
     "st2_attention": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "st2_attention_ex": [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],
+    "st2_attention_tc_supported": [_ll, _ll, _ll, _i],
+    "st2_attention_tc": [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],
     "st2_embedding_sum_rows": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp],
     "st2_lstm_bidir": [_vp, _vp, _vp, _ll, _ll, _ll, _vp, _i, _i, _i, _vp, _vp],
     "st2_kdiff_step": [_vp, _vp, _vp, _f, _f, _f, _f, _vp, _f, _vp, _f, _vp, _i, _vp],

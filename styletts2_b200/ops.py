@@ -370,11 +370,27 @@ def linear_strided(x, B, Lr, K, bs, ls, ks, W, bias=None, *, act=ACT_NONE, out=N
     return out
 
 
-def attention(q, kv, B, N, H=8, D=64):
-    out = empty(B * N, H * D, device=q.device)
-    with _prof(f"attention B{B} N{N} H{H} D{D}", 4.0 * B * H * N * N * D, 4.0 * B * N * H * D * 4):
-        L.call("st2_attention", ptr(q), ptr(kv), ptr(out), B, N, H, D, float(D) ** -0.5, stream_ptr())
+ATT_TC = os.environ.get("ST2_ATT_TC", "1") != "0"   # tcgen05 attention (fp32-accurate) where supported
+ATT_TC_MIN_N = 32
+
+
+def attention_ex(q, k, v, out, B, N, H, D, lengths=None):
+    """softmax(q k^T / sqrt(D)) v per (utterance, head).  q / k / v / out: 2-D row views [B*N, >= H*D] (row strides free,
+    head h in columns h*D..); lengths (int32 [B]) = key-padding mask.  tcgen05 kernel when the layout allows it."""
+    scale = float(D) ** -0.5
+    use_tc = (ATT_TC and USE_TC and N >= ATT_TC_MIN_N and k.stride(0) == v.stride(0)
+              and bool(L.load().st2_attention_tc_supported(q.stride(0), k.stride(0), out.stride(0), D))
+              and all(t.data_ptr() % 16 == 0 for t in (q, k, v, out)))
+    with _prof(f"attention{'_tc' if use_tc else ''} B{B} N{N} H{H} D{D}", 4.0 * B * H * N * N * D, 4.0 * B * N * H * D * 4, 3 if use_tc else 0):
+        L.call("st2_attention_tc" if use_tc else "st2_attention_ex", ptr(q), q.stride(0), ptr(k), ptr(v), k.stride(0), ptr(out),
+               out.stride(0), ptr(lengths), B, N, H, D, scale, stream_ptr())
     return out
+
+
+def attention(q, kv, B, N, H=8, D=64):
+    """q [B*N, H*D], kv [B*N, 2*H*D] (k | v) -> [B*N, H*D]   (Modules/diffusion/modules.py:523-535)"""
+    out = empty(B * N, H * D, device=q.device)
+    return attention_ex(q, kv[:, :H * D], kv[:, H * D:], out, B, N, H, D)
 
 
 def lstm_bidir(gx, whh, out, o_bs, o_ts, o_cs, B, Lr, H, lengths=None):

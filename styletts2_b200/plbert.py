@@ -115,8 +115,7 @@ class PLBert(nn.Module):
             use = wtc if M >= ops.LINEAR_TC_MIN_ROWS else None
             qkv = ops.linear(h, Wqkv, bqkv, wtc=use)                          # [M, 3*768] = q | k | v
             ctx = ops.empty(M, Hd, device=dev)
-            ops.L.call("st2_attention_ex", ops.ptr(qkv), qkv.stride(0), ops.ptr(qkv[:, Hd:]), ops.ptr(qkv[:, 2 * Hd:]), qkv.stride(0),
-                       ops.ptr(ctx), ctx.stride(0), ops.ptr(lengths), B, N, H, D, float(D) ** -0.5, ops.stream_ptr())
+            ops.attention_ex(qkv[:, :Hd], qkv[:, Hd:2 * Hd], qkv[:, 2 * Hd:], ctx, B, N, H, D, lengths)
             y = att.dense(ctx, R=h)                                           # hidden + dense(attn)
             a_out = ops.empty(M, Hd, device=dev)
             ops.rows_ln(B=B, N=N, Cw=Hd, h_in=y, g1=att.LayerNorm.weight, b1=att.LayerNorm.bias, out1=a_out, eps=cfg.layer_norm_eps)

@@ -63,12 +63,17 @@ if __name__ == "__main__":
     for (b, C, K, d, L, res) in shapes:
         fl = 2.0 * C * C * K * L * b
         print(f"== B{b} C{C} K{K} d{d} L{L} res={res}  ({fl / 1e9:.1f} GFLOP)")
-        for mode, name in ((0, "FAST"), (2, "F16X3"), (1, "ACC")):
+        for mode, name in (((0, "FAST"),) if os.environ.get("TC_BENCH_DEEP") else ((0, "FAST"), (2, "F16X3"), (1, "ACC"))):
             call = setup(b, C, K, d, L, res, mode)
             lib.call("st2_debug_set_flags", 0)
             ms = timeit(call)
             row = [f"{name}: {ms:.3f} ms ({fl / ms / 1e9:.0f} TF/s fp32-eq)"]
-            for flags, fn in ((1, "f16-2nd"), (2, "no-epi-io"), (4, "no-convert"), (8, "no-mma"), (2 | 4, "no-io+no-conv"), (2 | 4 | 8, "skeleton")):
+            variants = ((1, "f16-2nd"), (2, "no-epi-io"), (4, "no-convert"), (8, "no-mma"), (2 | 4, "no-io+no-conv"), (2 | 4 | 8, "skeleton"))
+            if mode == 0 and os.environ.get("TC_BENCH_DEEP"):
+                variants = ((2 | 4 | 8, "skeleton"), (2 | 4 | 8 | 16, "skel-noW"), (2 | 4 | 8 | 32, "skel-noRaw"), (2 | 4 | 8 | 16 | 32, "skel-handshake"),
+                            (4 | 8 | 16 | 32 | 64, "handshake-noEpi"), (16, "full-noW"), (64, "full-noEpi"), (16 | 64, "full-noW-noEpi"), (32, "full-noRaw"),
+                            (2, "no-epi-io"), (4, "no-convert"), (8, "no-mma"))
+            for flags, fn in variants:
                 if flags & 1 and mode != 0:
                     continue
                 lib.call("st2_debug_set_flags", flags)
