@@ -257,9 +257,9 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(const Args a) 
   }
   mbar_wait(bar_o, ph_o);
   tc_fence_after();
-  if (worker && row < N) {
+  if (worker) {     // tcgen05.ld is warp-collective: every lane of the worker warps runs the loads, only the stores are predicated
     const float inv = 1.0f / l;
-    float* orow = a.out + (rowbase + row) * a.out_ld + h * HD;
+    float* orow = a.out + (rowbase + min(row, N - 1)) * a.out_ld + h * HD;
 #pragma unroll
     for (int c0 = 0; c0 < HD; c0 += 32) {
       float o[32], t[32];
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(const Args a) 
         float4 w;
         w.x = fmaf(t[j], LO_UNSCALE, o[j]) * inv; w.y = fmaf(t[j + 1], LO_UNSCALE, o[j + 1]) * inv;
         w.z = fmaf(t[j + 2], LO_UNSCALE, o[j + 2]) * inv; w.w = fmaf(t[j + 3], LO_UNSCALE, o[j + 3]) * inv;
-        *reinterpret_cast<float4*>(orow + c0 + j) = w;
+        if (row < N) *reinterpret_cast<float4*>(orow + c0 + j) = w;
       }
     }
   }

@@ -53,9 +53,13 @@ constexpr int TN = 256;
 constexpr int TM = 128;
 constexpr int CB = 16;                          // input channels per pipeline block (one UMMA K step of the fp16 planes)
 constexpr int KCB = CB / 8;                     // 16-byte K chunks per plane and block
-constexpr int W_STAGES = 8;                     // 64 KB of weights in flight per SM
 constexpr int W_PLANE_BYTES = KCB * TM * 16;    // 4 KB
-constexpr int W_STAGE_BYTES = 2 * W_PLANE_BYTES;  // plane 0 (fp16 high) | plane 1 (fp8 corrections or fp16 low) = 8 KB
+constexpr int W_STEP_BYTES = 2 * W_PLANE_BYTES; // one (16 ci, tap) step: plane 0 (fp16 high) | plane 1 (fp8 corrections or fp16 low) = 8 KB
+constexpr int TPS = 2;                          // taps per pipeline stage: one wait / one commit / one bulk copy per 2 taps (the
+                                                // per-stage handshake of the two single-thread roles costs ~300 cycles, as much
+                                                // as the 2 MMAs of one tap: profiles/r02_tc_bench_*.txt)
+constexpr int W_STAGE_BYTES = TPS * W_STEP_BYTES;  // 16 KB
+constexpr int W_STAGES = 4;                     // 64 KB of weights in flight per SM
 constexpr int RW_MAX = 312;                     // TN + (K-1)*dil rounded up to 8, max
 constexpr int RWP_MAX = RW_MAX + 2;             // chunk pitch in rows of the staged planes
 constexpr int ACT_PLANE_BYTES = KCB * RWP_MAX * 16;  // one plane of one 16-channel block
@@ -308,12 +312,13 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           tc_fence_after();
           // descriptors differ from stage to stage only in their 14-bit start-address field (address >> 4, bits 0-13)
           const uint64_t db0_base = make_desc(sbase + SM_ACT + as * ACT_BUF_BYTES, lbo_b, 128);
-          for (int tap = 0; tap < K; ++tap) {
+          for (int tap0 = 0; tap0 < K; tap0 += TPS) {
             w_wf += wait_pumping(BAR(B_WFULL + ws), wph);
             tc_fence_after();
-            {
-              const uint64_t da0 = da_base + (uint64_t)(ws * (W_STAGE_BYTES >> 4)), da1 = da0 + (W_PLANE_BYTES >> 4);
-              const uint64_t db0 = db0_base + (uint64_t)(tap * dil_), db1 = db0 + (ACT_PLANE_BYTES >> 4);
+            const int nt = min(TPS, K - tap0);
+            for (int t = 0; t < nt; ++t) {
+              const uint64_t da0 = da_base + (uint64_t)(ws * (W_STAGE_BYTES >> 4) + t * (W_STEP_BYTES >> 4)), da1 = da0 + (W_PLANE_BYTES >> 4);
+              const uint64_t db0 = db0_base + (uint64_t)((tap0 + t) * dil_), db1 = db0 + (ACT_PLANE_BYTES >> 4);
               if (dbg & 8) {
               } else if (MODE == MODE_FAST) {
                 tc_mma(d0, da0, db0, idesc, first ? 0u : 1u);
@@ -340,26 +345,28 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       }
     }
   } else if (warp == 1) {
-    // ================================================================ weight producers (1-D TMA bulk copies)
-    // NPROD lanes, each owning every NPROD-th stage of the (tile, cb, tap) sequence: the wait -> expect_tx -> bulk-copy
-    // chain of one stage costs ~300 cycles of latency when a single thread runs it back to back (more than the 256
-    // tensor cycles a stage feeds); independent lanes overlap those latencies.
-    constexpr int NPROD = 1;   // (4 lanes of one warp were measured SLOWER than one: divergent spin loops serialise)
-    if (lane < NPROD) {
-      const int per_tile = ncb * K;
+    // ================================================================ weight producer (1-D TMA bulk copies)
+    // one copy per stage = up to TPS consecutive taps of one 16-channel block (contiguous in the [cob][cb][tap] layout)
+    if (lane == 0) {
       const int dbg_p = g_dbg;
-      const long long total = (long long)((ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * per_tile;
-      for (long long sidx = lane; sidx < total; sidx += NPROD) {
-        const int tl = (int)(sidx / per_tile), rem = (int)(sidx - (long long)tl * per_tile);
-        const int cb = rem / K, tap = rem - cb * K;
-        const int ws = (int)(sidx % W_STAGES);
-        const uint32_t wph = (uint32_t)((sidx / W_STAGES) & 1);
-        const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
-        mbar_wait(BAR(B_WEMPTY + ws), wph ^ 1);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(wtc) + ((size_t)((tap * n_cob + tc_.cob) * ncb + cb)) * W_STAGE_BYTES;
-        if (dbg_p & 16) { mbar_arrive(BAR(B_WFULL + ws)); continue; }     // timing experiment: no weight traffic
-        mbar_expect_tx(BAR(B_WFULL + ws), W_STAGE_BYTES);
-        bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, W_STAGE_BYTES, BAR(B_WFULL + ws));
+      int ws = 0, wph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(wtc) + (size_t)tc_.cob * ncb * K * W_STEP_BYTES;
+        for (int cb = 0; cb < ncb; ++cb) {
+          for (int tap0 = 0; tap0 < K; tap0 += TPS) {
+            const uint32_t bytes = (uint32_t)min(TPS, K - tap0) * W_STEP_BYTES;
+            mbar_wait(BAR(B_WEMPTY + ws), wph ^ 1);
+            if (dbg_p & 16) {
+              mbar_arrive(BAR(B_WFULL + ws));                    // timing experiment: no weight traffic
+            } else {
+              mbar_expect_tx(BAR(B_WFULL + ws), bytes);
+              bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, bytes, BAR(B_WFULL + ws));
+            }
+            src += bytes;
+            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+          }
+        }
       }
     }
   } else if (warp < 2 + NUM_STAGERS / 32) {
@@ -706,7 +713,7 @@ __device__ __forceinline__ void weight_stage_store(uint8_t* blk, int byte_in_sta
   }
 }
 
-// fp32 [Cout,Cin,K] -> stage blocks [K][n_cob][ncb] x 8 KB
+// fp32 [Cout,Cin,K] -> step blocks [n_cob][ncb][K] x 8 KB (the taps of one 16-channel block are contiguous)
 __global__ void conv_tc_weight_layout_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int Cout, int Cin, int K,
                                              int n_cob, int ncb, int mode) {
   // one thread per (stage, plane, chunk, row): writes the 16 bytes of that row
@@ -728,7 +735,7 @@ __global__ void conv_tc_weight_layout_kernel(const float* __restrict__ w, uint8_
       const int ci = cb * CB + j;
       wr[j] = (rr < rq && co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * K + tap] : 0.f;
     }
-    uint8_t* blk = out + ((long long)(tap * n_cob + cob) * ncb + cb) * W_STAGE_BYTES;
+    uint8_t* blk = out + (((long long)cob * ncb + cb) * K + tap) * W_STEP_BYTES;
     const int base = plane * W_PLANE_BYTES + (chunk * TM + col) * 16;
 #pragma unroll
     for (int b = 0; b < 16; ++b) weight_stage_store(blk, base + b, mode, wr);
@@ -759,7 +766,7 @@ __global__ void convT_tc_weight_layout_kernel(const float* __restrict__ w, uint8
       const int ci = cb * CB + j;
       wr[j] = (rr < rq && co < Cout && ci < Cin && kk < K) ? w[((long long)ci * Cout + co) * K + kk] : 0.f;
     }
-    uint8_t* blk = out + ((long long)ph * J * n_cob * ncb + (long long)(kp * n_cob + cob) * ncb + cb) * W_STAGE_BYTES;
+    uint8_t* blk = out + ((long long)ph * J * n_cob * ncb + ((long long)cob * ncb + cb) * J + kp) * W_STEP_BYTES;
     const int base = plane * W_PLANE_BYTES + (chunk * TM + col) * 16;
 #pragma unroll
     for (int b = 0; b < 16; ++b) weight_stage_store(blk, base + b, mode, wr);
@@ -798,7 +805,7 @@ extern "C" {
 
 long long st2_conv_tc_weight_bytes(int Cout, int Cin, int K) {
   const int n_cob = cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB);
-  return (long long)K * n_cob * ncb * tc::W_STAGE_BYTES;
+  return (long long)K * n_cob * ncb * tc::W_STEP_BYTES;
 }
 
 static bool tc_mode_ok(int mode) { return mode == ST2_TC_FAST || mode == ST2_TC_ACCURATE || mode == ST2_TC_F16X3; }
