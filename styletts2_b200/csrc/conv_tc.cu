@@ -285,7 +285,63 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
 
   if (warp == 0) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    // Production path: the whole warp stays converged (every lane waits on the barriers), ONE elected lane issues the
+    // MMAs and commits; every quantity is warp-uniform, descriptors are (low, high) words and a tap only bumps the low
+    // word.  [A single lane walking the generic loop below spends ~250 cycles of dependent instructions per tap -- as
+    // long as the two MMAs of a tap take on the tensor pipe (profiles/r02_tc_bench_*.txt).]
+    if (g_dbg == 0 && !(g_trace != nullptr && blockIdx.x == 0)) {
+      const uint32_t idesc = make_idesc();
+      const uint32_t elected = elect_one();
+      const uint64_t da_d = make_desc(sbase + SM_W, TM * 16, 128), db_d = make_desc(sbase + SM_ACT, (uint32_t)RWP * 16, 128);
+      const uint32_t da_lo0 = (uint32_t)da_d, da_hi = (uint32_t)(da_d >> 32), db_lo0 = (uint32_t)db_d, db_hi = (uint32_t)(db_d >> 32);
+      const uint32_t dil_ = (uint32_t)a.dil;
+      int ws = 0, wph = 0, as = 0, aph = 0, it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it % NBUF;
+        mbar_wait(BAR(B_TEMPTY + buf), ((it / NBUF) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)buf * TN;
+        const uint32_t d1 = (MODE == MODE_ACC) ? tmem_base + TN : d0;
+        uint32_t acc = 0;
+        for (int cb = 0; cb < ncb; ++cb) {
+          mbar_wait(BAR(B_AFULL + as), aph);
+          tc_fence_after();
+          uint32_t b_lo = db_lo0 + (uint32_t)as * (ACT_BUF_BYTES >> 4);
+          for (int tap0 = 0; tap0 < K; tap0 += TPS) {
+            mbar_wait(BAR(B_WFULL + ws), wph);
+            tc_fence_after();
+            if (elected) {
+              uint32_t a_lo = da_lo0 + (uint32_t)ws * (W_STAGE_BYTES >> 4);
+              const int nt = min(TPS, K - tap0);
+#pragma unroll
+              for (int t = 0; t < TPS; ++t) {
+                if (t < nt) {
+                  if (MODE == MODE_FAST) {
+                    tc_mma_w(d0, a_lo, da_hi, b_lo, db_hi, idesc, acc);
+                    tc_mma_f8_w(d0, a_lo + (W_PLANE_BYTES >> 4), da_hi, b_lo + (ACT_PLANE_BYTES >> 4), db_hi, idesc, 1u);
+                  } else {
+                    tc_mma_w(d0, a_lo, da_hi, b_lo, db_hi, idesc, acc);
+                    tc_mma_w(d1, a_lo, da_hi, b_lo + (ACT_PLANE_BYTES >> 4), db_hi, idesc, MODE == MODE_ACC ? acc : 1u);
+                    tc_mma_w(d1, a_lo + (W_PLANE_BYTES >> 4), da_hi, b_lo, db_hi, idesc, 1u);
+                  }
+                  acc = 1;
+                  a_lo += W_STEP_BYTES >> 4;
+                  b_lo += dil_;
+                }
+              }
+              tc_commit(BAR(B_WEMPTY + ws));
+            } else {
+              acc = 1;
+              b_lo += dil_ * (uint32_t)min(TPS, K - tap0);
+            }
+            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+          }
+          if (elected) tc_commit(BAR(B_AEMPTY + as));
+          if (++as == 2) { as = 0; aph ^= 1; }
+        }
+        if (elected) tc_commit(BAR(B_TFULL + buf));
+      }
+    } else if (lane == 0) {
       const uint32_t idesc = make_idesc();
       const uint32_t lbo_a = TM * 16, lbo_b = (uint32_t)RWP * 16;
       const int dbg = g_dbg;
@@ -459,6 +515,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
         // the 2^6 operand scale is folded into the coefficients: z' = 64 z = (64a) x + 64b; snake(z) * 64 =
         // z' + (64/alpha) sin^2((alpha/64) z'); LeakyReLU is positively homogeneous
         const float* cf = reinterpret_cast<const float*>(smem + SM_COEF + (g % RAW_STAGES) * COEF_BYTES) + kc * 8;
+        const int sh0 = (int)((xaddr4 + (unsigned long long)(c_boff + (long long)c0 * Lin_ + c_g0)) & 3ull), lin3 = Lin_ & 3;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const bool cv = (c0 + j) < Cin_;
@@ -468,8 +525,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           pb[j] = cf[CB + j] * xs_;
           al[j] = al_ * (1.0f / X_SCALE);
           ia[j] = __frcp_rn(al_) * xs_;
-          const long long e0 = c_boff + (long long)min(c0 + j, Cin_ - 1) * Lin_ + c_g0;
-          sh[j] = (int)((xaddr4 + (unsigned long long)e0) & 3ull) + j * RAW_PITCH;
+          sh[j] = ((sh0 + j * lin3) & 3) + j * RAW_PITCH;   // 4-byte phase of channel c0+j's row start (padded channels: any)
         }
       }
       const float* raw = reinterpret_cast<const float*>(smem + SM_RAW + (g % RAW_STAGES) * RAW_BYTES) + (kc * 8) * RAW_PITCH;
