@@ -594,6 +594,24 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           }
         }
       }
+      // Residual values of one 32x32 block: lane = column, rv[r] = row r.  The loads of block c+1 are issued right after
+      // the row loop of block c has consumed rv (same registers): their latency hides behind the statistics of block c
+      // and the TMEM load / transpose of block c+1; the first block's loads fly during the wait for the accumulator.
+      float rv[32];
+      auto load_rv = [&](int c0) {
+        const int tcol = t0 + c0 + lane;
+        const bool okc = (c0 + lane) < ncols;
+        const float* rp0 = rb ? rb + ((tcol * ytst_ + ytoff_) >> rshift_) : nullptr;
+        const unsigned rl = (unsigned)res_len_;
+        if (rb && rmax == 32 && (c0 + 32) <= ncols && !dbg_noio) {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) rv[r] = __ldg(rp0 + (unsigned)r * rl);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) rv[r] = (rb && okc && r < rmax && !dbg_noio) ? __ldg(rp0 + (unsigned)r * rl) : 0.f;
+        }
+      };
+      load_rv(half * (TN / 2));
       const long long ett0 = clock64();
       const long long w_tf = mbar_wait_timed(BAR(B_TFULL + buf), (it / NBUF) & 1);
       tc_fence_after();
@@ -603,20 +621,6 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       for (int c0 = half * (TN / 2); c0 < (half + 1) * (TN / 2); c0 += 32) {
         float v[32];
         const long long q0 = clock64();
-        float rv[32];
-        {
-          const int tcol = t0 + c0 + lane;
-          const bool okc = (c0 + lane) < ncols;
-          const float* rp0 = rb ? rb + ((tcol * ytst_ + ytoff_) >> rshift_) : nullptr;
-          const unsigned rl = (unsigned)res_len_;
-          if (rb && rmax == 32 && (c0 + 32) <= ncols && !dbg_noio) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) rv[r] = __ldg(rp0 + (unsigned)r * rl);
-          } else {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) rv[r] = (rb && okc && r < rmax && !dbg_noio) ? __ldg(rp0 + (unsigned)r * rl) : 0.f;
-          }
-        }
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + c0);
         tmem_ld32(taddr, v);
         if (MODE == MODE_ACC) {
@@ -675,6 +679,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
             }
           }
         }
+        if (c0 + 32 < (half + 1) * (TN / 2)) load_rv(c0 + 32);
         const long long q2 = clock64();
         tr_st += q2 - q1;
         // ReflectionPad1d((1,0)) duplicate of the q==0 column (istftnet.py:365-366): value differs by its residual

@@ -56,6 +56,15 @@ constexpr int B_WFULL = 0, B_WEMPTY = 6, B_AFULL = 12, B_AEMPTY = 16, B_TFULL = 
 
 using namespace st2::ptx;
 
+// Range guard: the fp16 planes hold |x| < 65504; larger activations become inf (and the product NaN/inf).  Every thread
+// that splits activations tracks its own maximum and raises this flag once; st2_range_flag_fetch() reports and clears
+// it (the host checks it after a pass, styletts2_b200.ops.check_range).  Weights are checked when they are laid out.
+__device__ int g_range_flag = 0;
+constexpr float FP16_MAX = 65504.0f;
+__device__ __forceinline__ void range_note(float amax) {
+  if (!(amax < FP16_MAX)) atomicExch(&g_range_flag, 1);   // also catches NaN
+}
+
 __device__ __forceinline__ uint32_t make_idesc() {
   uint32_t d = 0;
   d |= 1u << 4;                      // D = F32;  A = B = F16 (format code 0 in bits 7-9 / 10-12)
@@ -214,7 +223,10 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
         }
       };
       load_blk(0, cur);
+      float amax = 0.f;
       for (int cb = 0; cb < ncb; ++cb) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(cur[q].x), fabsf(cur[q].y)), fmaxf(fabsf(cur[q].z), fabsf(cur[q].w))));
         if (cb + 1 < ncb) load_blk(cb + 1, nxt);
         mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
         uint8_t* base = smem + SM_A + as * A_BUF_BYTES;
@@ -237,6 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
 #pragma unroll
         for (int q = 0; q < 4; ++q) cur[q] = nxt[q];
       }
+      range_note(amax);
     }
   } else {
     // ================================================================ epilogue (4 warps; lane = out feature)
@@ -318,6 +331,10 @@ __global__ void linear_tc_split_kernel(const float* __restrict__ A, long long ld
           if (k0 + j < K) x[j] = __ldg(p + j);
       }
     }
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(x[j]));
+    range_note(amax);
     uint32_t p0[4], p1[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) split2(x[2 * q], x[2 * q + 1], p0[q], p1[q]);
@@ -343,6 +360,7 @@ __global__ void linear_tc_weight_layout_kernel(const float* __restrict__ w, __ha
     const int n = cob * TMF + col, k = cb * KB + kc * 8 + j;
     float v = 0.f;
     if (n < Nf && k < K) v = w[(long long)n * K + k];
+    range_note(fabsf(v));
     const __half h0 = __float2half_rn(v);
     const __half h1 = __float2half_rn((v - __half2float(h0)) * LO_SCALE);
     out[i] = pl == 0 ? h0 : h1;
@@ -355,6 +373,16 @@ __global__ void linear_tc_weight_layout_kernel(const float* __restrict__ w, __ha
 using namespace st2;
 
 extern "C" {
+
+int st2_range_flag_fetch(int* flag_out) {
+  ST2_REQUIRE(flag_out, "st2_range_flag_fetch", "bad args");
+  int v = 0, zero = 0;
+  cudaError_t e = cudaMemcpyFromSymbol(&v, ltc::g_range_flag, sizeof(int));     // synchronises with the device
+  if (e == cudaSuccess && v) e = cudaMemcpyToSymbol(ltc::g_range_flag, &zero, sizeof(int));
+  if (e != cudaSuccess) { set_error("st2_range_flag_fetch", e); return (int)e; }
+  *flag_out = v;
+  return 0;
+}
 
 long long st2_linear_tc_weight_bytes(int Nf, int K) {
   return (long long)cdiv(Nf, ltc::TMF) * cdiv(K, ltc::KB) * ltc::W_STAGE_BYTES;

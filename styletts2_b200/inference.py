@@ -187,6 +187,8 @@ class Synthesizer:
                 Ncurve[ii, :2 * Tg] = n_
                 wl[idx] = 600 * Tg
             out = dict(wav=wav, pred_dur=pred_dur, T=T, s_carry=s_carry, wav_lengths=wl)
+        if not torch.cuda.is_current_stream_capturing() and (forced_durations is not None or pin_frames_per_token is None):
+            ops.check_range()     # fp16-plane range guard of the tensor-core GEMMs (the path has synchronised already)
         if return_all:
             out.update(t_en=t_en, d_en=d_en_rows.transpose(-1, -2), s_pred=s_pred, s=s, ref=ref, d=d, logits=logits,
                        dur_f=dur_f, en=None if en_rows is None else en_rows.transpose(-1, -2), asr=asr, F0=F0, N=Ncurve)

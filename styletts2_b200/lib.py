@@ -90,6 +90,7 @@ SIGNATURES = {
     "st2_linear_tc_pre": [_vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp],
     "st2_linear_tc_split": [_vp, _ll, _i, _i, _vp, _vp],
     "st2_linear_tc_split_bytes": [_i, _i],
+    "st2_range_flag_fetch": [_vp],
     "st2_attention": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "st2_attention_ex": [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp],
     "st2_attention_tc_supported": [_ll, _ll, _ll, _i],

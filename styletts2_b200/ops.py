@@ -359,6 +359,16 @@ def linear(A, W, bias=None, *, act=ACT_NONE, R=None, out=None, wtc=None):
     return out
 
 
+def check_range():
+    """Raise if any fp16-plane GEMM operand since the last check left fp16's range (|x| >= 65504 or NaN): the outputs of
+    that pass hold inf/NaN.  Synchronises; not callable under CUDA-graph capture."""
+    flag = C.c_int(0)
+    L.call("st2_range_flag_fetch", C.byref(flag))
+    if flag.value:
+        raise FloatingPointError("styletts2_b200: an activation or weight of a tensor-core GEMM exceeded the fp16 plane range "
+                                 "(|x| >= 65504) or was NaN; set ST2_TC=0 to run these GEMMs on the fp32 SIMT kernels")
+
+
 def linear_strided(x, B, Lr, K, bs, ls, ks, W, bias=None, *, act=ACT_NONE, out=None):
     """Rows (b,l) of x addressed with explicit strides (conv-layout inputs of LSTM projections)."""
     Nf = W.shape[0]

@@ -173,3 +173,22 @@ def test_linear_tc_wide_dynamic_range():
     e_32 = float(((y32 - ref).abs() / bound).max())
     record("linear_tc_dynamic_range", err_over_sum_abs_tc=e_tc, err_over_sum_abs_fp32_simt=e_32)
     assert e_tc < 1.5e-6, (e_tc, e_32)       # fp32 SIMT lands at ~1e-7..1e-6 on the same data
+
+
+def test_linear_tc_range_guard_reports_fp16_plane_overflow():
+    """|x| >= 65504 cannot be held by the fp16 planes: the GEMM output turns inf/NaN (loud) AND the library's range flag is
+    raised, which ops.check_range() turns into an exception (Synthesizer.synthesize checks it after every non-graph pass)."""
+    from styletts2_b200 import ops
+    M, K, Nf = 300, 256, 128
+    A, W = rnd(M, K, seed=1), rnd(Nf, K, seed=2, scale=1 / math.sqrt(K))
+    Wd = W.to(D)
+    wtc = ops.linear_tc_weight_layout(Wd)
+    ops.check_range()                                   # clean so far (also clears)
+    ops.linear(A.to(D), Wd, None, wtc=wtc)
+    ops.check_range()
+    A[7, 3] = 1.0e5
+    y = ops.linear(A.to(D), Wd, None, wtc=wtc)
+    assert not torch.isfinite(y[7]).all()
+    with pytest.raises(FloatingPointError):
+        ops.check_range()
+    ops.check_range()                                   # the fetch cleared the flag

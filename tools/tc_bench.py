@@ -69,6 +69,8 @@ if __name__ == "__main__":
             ms = timeit(call)
             row = [f"{name}: {ms:.3f} ms ({fl / ms / 1e9:.0f} TF/s fp32-eq)"]
             variants = ((1, "f16-2nd"), (2, "no-epi-io"), (4, "no-convert"), (8, "no-mma"), (2 | 4, "no-io+no-conv"), (2 | 4 | 8, "skeleton"))
+            if os.environ.get("TC_BENCH_QUICK"):
+                variants = ()
             if mode == 0 and os.environ.get("TC_BENCH_DEEP"):
                 variants = ((2 | 4 | 8, "skeleton"), (2 | 4 | 8 | 16, "skel-noW"), (2 | 4 | 8 | 32, "skel-noRaw"), (2 | 4 | 8 | 16 | 32, "skel-handshake"),
                             (4 | 8 | 16 | 32 | 64, "handshake-noEpi"), (16, "full-noW"), (64, "full-noEpi"), (16 | 64, "full-noW-noEpi"), (32, "full-noRaw"),
