@@ -126,6 +126,12 @@ int st2_debug_set_flags(int flags);
 long long st2_convT_tc_weight_bytes(int Cin, int Cout, int K, int S);
 int st2_convT_tc_weight_layout(const float* w, void* out, int Cin, int Cout, int K, int S, int P, int mode, void* stream);
 int st2_conv_transpose1d_tc(const st2_conv_args* a, const void* wtc, int mode, int K, int S, int P, int reflect_left1, void* stream);
+/* Same result through a phase-major scratch buffer: the S phase convolutions store contiguous rows into `tmp`
+ * (S*B*Cout*Lin floats, caller-owned), then one memory-bound kernel interleaves the phases into y, adds the residual
+ * (a->res), applies the reflection duplicate and writes ONE statistics record per (b, co) (a->stats [B,Cout,1,3],
+ * stats_nparts == 1).  Strided 4-byte epilogue stores of the direct variant cost 6-10x the interleave pass. */
+int st2_conv_transpose1d_tc2(const st2_conv_args* a, const void* wtc, int mode, int K, int S, int P, int reflect_left1, float* tmp,
+                             void* stream);
 
 /* ConvTranspose1d (stride S, K taps, padding P; output length Lin*S) as S polyphase
  * stride-1 convolutions through the same fused kernel; `a` describes the x / y / prologue /

@@ -834,6 +834,67 @@ __global__ void convT_tc_weight_layout_kernel(const float* __restrict__ w, uint8
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Polyphase ConvTranspose1d, second half: the S phase convolutions write PHASE-MAJOR rows tmp[r][b][co][q] (coalesced
+// epilogue stores); this kernel interleaves them into y[b][co][q*S + r (+1)], adds the residual, applies the
+// ReflectionPad1d((1,0)) duplicate (istftnet.py:365-366: y[0] = y[2], i.e. the unpadded sample 1 = phase 1, q = 0) and
+// produces the InstanceNorm statistics of the result: per-thread Welford in fp64, fixed-order Chan merge -> one
+// (count, mean, M2) record per row.  Memory-bound: reads tmp + res, writes y.
+__global__ void __launch_bounds__(256) convT_interleave_kernel(const float* __restrict__ tmp, long long phase_stride, const float* __restrict__ res,
+                                                               long long res_bstride, int res_len, float* __restrict__ y, long long y_bstride,
+                                                               int y_len, int C, int Lin, int S, int reflect, float* __restrict__ stats) {
+  const int co = blockIdx.x, b = blockIdx.y;
+  const float* trow = tmp + ((long long)b * C + co) * Lin;
+  const float* rrow = res ? res + (long long)b * res_bstride + (long long)co * res_len : nullptr;
+  float* yrow = y + (long long)b * y_bstride + (long long)co * y_len;
+  const int Lout = Lin * S + reflect;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int o = threadIdx.x; o < Lout; o += blockDim.x) {
+    int u = o - reflect;            // index in the unpadded transposed-conv output
+    if (u < 0) u = 1;               // reflection of the left edge
+    const int q = u / S, r = u - q * S;
+    float v = trow[(long long)r * phase_stride + q];
+    if (rrow) v += rrow[o];
+    yrow[o] = v;
+    n += 1.0;
+    const double d = (double)v - mean;
+    mean += d / n;
+    m2 += d * ((double)v - mean);
+  }
+  if (!stats) return;
+  // merge: lanes, then warps (fixed order)
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double nb = __shfl_down_sync(0xffffffffu, n, off), mb = __shfl_down_sync(0xffffffffu, mean, off),
+                 qb = __shfl_down_sync(0xffffffffu, m2, off);
+    const double nn = n + nb;
+    if (nn > 0.0) {
+      const double dl = mb - mean;
+      mean += dl * (nb / nn);
+      m2 += qb + dl * dl * (n * nb / nn);
+      n = nn;
+    }
+  }
+  __shared__ double sn[8], sm[8], sq[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { sn[w] = n; sm[w] = mean; sq[w] = m2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double N = sn[0], M = sm[0], Q = sq[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) {
+      const double nn = N + sn[i];
+      if (nn > 0.0) {
+        const double dl = sm[i] - M;
+        M += dl * (sn[i] / nn);
+        Q += sq[i] + dl * dl * (N * sn[i] / nn);
+        N = nn;
+      }
+    }
+    float* sp = stats + ((long long)b * C + co) * 3;
+    sp[0] = (float)N; sp[1] = (float)M; sp[2] = (float)Q;
+  }
+}
+
 static int launch_tc(const st2_conv_args& a, const void* wtc, int mode, int max_ctas, cudaStream_t st) {
   const int n_tq = cdiv(a.Lq, TN), n_cob = cdiv(a.Cout, TM), ncb = cdiv(a.Cin, CB);
   const int rw = (TN + (a.K - 1) * a.dil + 7) & ~7;
@@ -948,6 +1009,46 @@ int st2_conv_transpose1d_tc(const st2_conv_args* a0, const void* wtc, int mode, 
     tc::launch_tc(a, (const uint8_t*)wtc + (size_t)r * phase_bytes, mode, 0, (cudaStream_t)stream);
   }
   ST2_CHECK_LAUNCH("st2_conv_transpose1d_tc");
+  return 0;
+}
+
+/* Phase-major variant: every phase writes contiguous rows into `tmp` ([S][B][Cout][Lin] floats), one memory-bound pass
+ * interleaves, adds the residual and produces ONE statistics record per row (stats [B,Cout,1,3]). */
+int st2_conv_transpose1d_tc2(const st2_conv_args* a0, const void* wtc, int mode, int K, int S, int P, int reflect_left1, float* tmp,
+                             void* stream) {
+  ST2_REQUIRE(a0 && a0->x && wtc && a0->y && tmp && tc_mode_ok(mode), "st2_conv_transpose1d_tc2", "null pointer / bad mode");
+  ST2_REQUIRE(K > 0 && S > 0 && P >= 0, "st2_conv_transpose1d_tc2", "bad shape");
+  const int J = (K + S - 1) / S;
+  ST2_REQUIRE(st2_conv_tc_supported(a0->Cin, a0->Cout, J, 1, 1), "st2_conv_transpose1d_tc2", "unsupported shape");
+  ST2_REQUIRE(!a0->stats || a0->stats_nparts == 1, "st2_conv_transpose1d_tc2", "stats must have exactly one partial per row");
+  const long long phase_bytes = st2_conv_tc_weight_bytes(a0->Cout, a0->Cin, J);
+  const long long phase_stride = (long long)a0->B * a0->Cout * a0->Lin;
+  for (int r = 0; r < S; ++r) {
+    st2_conv_args a = *a0;
+    const int cr = (r + P) / S;
+    a.K = J;
+    a.stride = 1;
+    a.dil = 1;
+    a.pad = (J - 1) - cr;
+    a.Lq = a0->Lin;
+    a.y = tmp + (long long)r * phase_stride;
+    a.y_bstride = (long long)a0->Cout * a0->Lin;
+    a.y_tstride = 1;
+    a.y_toffset = 0;
+    a.y_len = a0->Lin;
+    a.res = nullptr;
+    a.stats = nullptr;
+    a.accum_mode = 0;
+    a.out_div = 1.0f;
+    a.dup_q0_to = -1;
+    tc::launch_tc(a, (const uint8_t*)wtc + (size_t)r * phase_bytes, mode, 0, (cudaStream_t)stream);
+  }
+  const int y_len = a0->Lin * S + (reflect_left1 ? 1 : 0);
+  tc::convT_interleave_kernel<<<dim3(a0->Cout, a0->B), 256, 0, (cudaStream_t)stream>>>(
+      tmp, phase_stride, a0->res, a0->res_bstride, a0->res_len, a0->y, a0->y_bstride, y_len, a0->Cout, a0->Lin, S, reflect_left1 ? 1 : 0,
+      a0->stats);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_conv_transpose1d_tc2");
   return 0;
 }
 

@@ -115,10 +115,16 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
 
   if (warp == 0) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    // the whole warp stays converged on the barrier waits, ONE elected lane issues; descriptors as (low, high) words so
+    // that a K step only bumps the low word (see conv_tc.cu: a lone lane walking a generic loop costs as many cycles in
+    // dependent instructions as the MMAs of a stage take on the tensor pipe)
+    {
       const uint32_t idesc = make_idesc();
+      const uint32_t elected = elect_one();
       const uint32_t lbo_a = TMF * 16, lbo_b = (a.planes ? TNT : RWP) * 16;
-      const uint32_t a_plane = a.planes ? (uint32_t)PRE_PLANE_BYTES : (uint32_t)A_PLANE_BYTES;
+      const uint32_t a_plane16 = (a.planes ? (uint32_t)PRE_PLANE_BYTES : (uint32_t)A_PLANE_BYTES) >> 4;
+      const uint64_t da_d = make_desc(sbase + SM_W, lbo_a, 128), db_d = make_desc(sbase + SM_A, lbo_b, 128);
+      const uint32_t da_lo0 = (uint32_t)da_d, da_hi = (uint32_t)(da_d >> 32), db_lo0 = (uint32_t)db_d, db_hi = (uint32_t)(db_d >> 32);
       int ws = 0, wph = 0, as = 0, aph = 0, it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
@@ -130,32 +136,30 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
         // bf16 version: 4.4e-6 -> fp32-SIMT level at K=1024).
         const uint32_t d_hi = tmem_base + (uint32_t)buf * (2 * TNT);
         const uint32_t d_lo = d_hi + TNT;
-        uint32_t first = 1;
+        uint32_t acc = 0;
         for (int cb = 0; cb < ncb; ++cb) {
           mbar_wait(BAR(B_AFULL + as), aph);
           mbar_wait(BAR(B_WFULL + ws), wph);
           tc_fence_after();
-          const uint32_t wb = sbase + SM_W + ws * W_STAGE_BYTES;
-          const uint32_t ab = sbase + SM_A + as * A_BUF_BYTES;
+          if (elected) {
+            const uint32_t wa = da_lo0 + (uint32_t)ws * (W_STAGE_BYTES >> 4), ab = db_lo0 + (uint32_t)as * (A_BUF_BYTES >> 4);
 #pragma unroll
-          for (int k16 = 0; k16 < 2; ++k16) {
-            uint64_t da[NPL], db[NPL];
-#pragma unroll
-            for (int p = 0; p < NPL; ++p) {
-              da[p] = make_desc(wb + p * W_PLANE_BYTES + (2 * k16) * lbo_a, lbo_a, 128);
-              db[p] = make_desc(ab + p * a_plane + (2 * k16) * lbo_b, lbo_b, 128);
+            for (int k16 = 0; k16 < 2; ++k16) {
+              const uint32_t a0 = wa + (uint32_t)(2 * k16) * (lbo_a >> 4), a1 = a0 + (W_PLANE_BYTES >> 4);
+              const uint32_t b0 = ab + (uint32_t)(2 * k16) * (lbo_b >> 4), b1 = b0 + a_plane16;
+              tc_mma_w(d_hi, a0, da_hi, b0, db_hi, idesc, acc);
+              tc_mma_w(d_lo, a0, da_hi, b1, db_hi, idesc, acc);
+              tc_mma_w(d_lo, a1, da_hi, b0, db_hi, idesc, 1u);
+              acc = 1;
             }
-            tc_mma(d_hi, da[0], db[0], idesc, first ? 0u : 1u);
-            tc_mma(d_lo, da[0], db[1], idesc, first ? 0u : 1u);
-            first = 0;
-            tc_mma(d_lo, da[1], db[0], idesc, 1u);
+            tc_commit(BAR(B_WEMPTY + ws));
+            tc_commit(BAR(B_AEMPTY + as));
           }
-          tc_commit(BAR(B_WEMPTY + ws));
-          tc_commit(BAR(B_AEMPTY + as));
+          acc = 1;
           if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
           if (++as == A_BUFS) { as = 0; aph ^= 1; }
         }
-        tc_commit(BAR(B_TFULL + buf));
+        if (elected) tc_commit(BAR(B_TFULL + buf));
       }
     }
   } else if (warp == 1) {

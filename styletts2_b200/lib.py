@@ -75,6 +75,7 @@ SIGNATURES = {
     "st2_convT_tc_weight_bytes": [_i, _i, _i, _i],
     "st2_convT_tc_weight_layout": [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "st2_conv_transpose1d_tc": [C.POINTER(ConvArgs), _vp, _i, _i, _i, _i, _i, _vp],
+    "st2_conv_transpose1d_tc2": [C.POINTER(ConvArgs), _vp, _i, _i, _i, _i, _i, _vp, _vp],
     "st2_conv_transpose1d": [C.POINTER(ConvArgs), _vp, _i, _i, _i, _i, _vp],
     "st2_instance_stats": [_vp, _ll, _i, _i, _i, _vp, _vp],
     "st2_adain_coef": [_vp, _i, _vp, _ll, _i, _i, _f, _vp, _vp, _vp],

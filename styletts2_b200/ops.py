@@ -124,6 +124,7 @@ class _prof:
         return False
 
 
+CONVT_PHASE_MAJOR = os.environ.get("ST2_CONVT_PHASE_MAJOR", "1") != "0"   # tensor-core ConvTranspose through a phase-major scratch buffer
 USE_TC = os.environ.get("ST2_TC", "1") != "0"   # tensor-core (tcgen05) conv path where a wtc buffer is given
 TC_MIN_WORK = 1 << 22                            # below this many MACs per utterance the SIMT kernel is used
 
@@ -213,7 +214,8 @@ def conv_transpose1d(x, wp, bias, *, K, stride, padding, pre_act=ACT_NONE, slope
     if out is None:
         out = empty(B, Cout, Lout, device=x.device)
     use_tc = wtc is not None and USE_TC
-    nparts = S * stats_parts(Lin) * (2 if use_tc else 1)
+    phase_major = use_tc and CONVT_PHASE_MAJOR and out.stride(2) == 1 and out.stride(1) == Lout
+    nparts = 1 if phase_major else S * stats_parts(Lin) * (2 if use_tc else 1)
     stats = empty(B, Cout, nparts, 3, device=x.device) if want_stats else None
     a = ConvArgs()
     _fill_conv_args(a, x, wp, bias, out, K=1, stride=1, dil=1, pad=0, Lq=Lin, y_len=Lout, pre=None, pre_act=pre_act,
@@ -224,7 +226,12 @@ def conv_transpose1d(x, wp, bias, *, K, stride, padding, pre_act=ACT_NONE, slope
     flops = 2.0 * B * Cin * Cout * J * S * Lin
     if use_tc:
         with _prof(f"convT_tc m{wtc.mode} ci{Cin} co{Cout} k{K} s{S} L{Lin} B{B}", flops, nbytes, 2 if wtc.mode == TC_FAST else 3):
-            L.call("st2_conv_transpose1d_tc", C.byref(a), ptr(wtc.buf), wtc.mode, K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
+            if phase_major:
+                tmp = empty(S * B * Cout * Lin, device=x.device)
+                L.call("st2_conv_transpose1d_tc2", C.byref(a), ptr(wtc.buf), wtc.mode, K, S, padding, 1 if reflect_left1 else 0, ptr(tmp),
+                       stream_ptr())
+            else:
+                L.call("st2_conv_transpose1d_tc", C.byref(a), ptr(wtc.buf), wtc.mode, K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
     else:
         with _prof(f"convT_simt ci{Cin} co{Cout} k{K} s{S} L{Lin} B{B}", flops, nbytes):
             L.call("st2_conv_transpose1d", C.byref(a), ptr(wp), K, S, padding, 1 if reflect_left1 else 0, stream_ptr())
