@@ -311,7 +311,10 @@ def run_ours(args):
     den = {}
     if "linear_tc" in fam:
         f_ = fam["linear_tc"]
-        att = fam.get("attention", dict(ms=0.0, flops=0.0))
+        att = dict(ms=0.0, flops=0.0)
+        for k_ in ("attention", "attention_tc"):
+            for kk in att:
+                att[kk] += fam.get(k_, {}).get(kk, 0.0)
         den = {"linear_tc_ms": round(f_["ms"], 3), "linear_tc_fp32_tflops": round(f_["flops"] / (f_["ms"] / 1e3) / 1e12, 1),
                "linear_tc_executed_tflops": round(f_["exec_flops"] / (f_["ms"] / 1e3) / 1e12, 1),
                "attention_ms": round(att["ms"], 3),

@@ -269,6 +269,11 @@ int st2_durations(const float* logits, int B, int N, int J, int last_plus, const
 /* frame -> token map from durations: tok[b,t] for t < T (T = row length), exclusive scan per utterance;
  * frames beyond sum(dur[b]) map to the last token.  total[b] = sum(dur[b]). */
 int st2_frame_tokens(const int* dur, int B, int N, int T, int shift_right, int* tok, int* total, void* stream);
+/* Polyphase view of a conv input for STRIDED convolutions (noise_convs of the generators, istftnet.py:334-343 /
+ * hifigan.py:298-302: kernel 2*stride, stride S): xp[b, c*S + r, q] = x[b, c, q*S + r - pad], q < Lp (zero outside).
+ * conv1d(x, w, stride=S, padding=pad) with K = J*S taps == conv1d(xp[..., :Lout + J - 1], wp, stride=1, padding=0) with
+ * wp[co, c*S + r, j] = w[co, c, j*S + r]: the strided conv then runs on the tensor-core kernel. */
+int st2_polyphase_gather(const float* x, long long x_bstride, int B, int C, int L, int S, int pad, int Lp, float* xp, void* stream);
 /* alignment expansion (d^T @ aln, t_en @ aln; #cell17) as a gather:
  *  rows: out[(b,t), c] = src[(b,tok[b,t]), c]      src row layout [B*N, C] (ld)
  *  cl  : out[b,c,t]    = src[b,c,tok[b,t]]         src conv layout [B,C,N] */

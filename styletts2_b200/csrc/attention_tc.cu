@@ -78,7 +78,7 @@ __device__ __forceinline__ void store_row8(uint8_t* plane0, int plane_bytes, siz
 
 __global__ void __launch_bounds__(THREADS, 1) attention_tc_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_s = sbase + SM_BAR, bar_o = sbase + SM_BAR + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 16);

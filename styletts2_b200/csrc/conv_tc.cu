@@ -59,7 +59,7 @@ constexpr int TPS = 2;                          // taps per pipeline stage: one 
                                                 // per-stage handshake of the two single-thread roles costs ~300 cycles, as much
                                                 // as the 2 MMAs of one tap: profiles/r02_tc_bench_*.txt)
 constexpr int W_STAGE_BYTES = TPS * W_STEP_BYTES;  // 16 KB
-constexpr int W_STAGES = 4;                     // 64 KB of weights in flight per SM
+constexpr int W_STAGES = 3;                     // 48 KB (6 taps) of weights in flight per SM
 constexpr int RW_MAX = 312;                     // TN + (K-1)*dil rounded up to 8, max
 constexpr int RWP_MAX = RW_MAX + 2;             // chunk pitch in rows of the staged planes
 constexpr int ACT_PLANE_BYTES = KCB * RWP_MAX * 16;  // one plane of one 16-channel block
@@ -83,11 +83,9 @@ constexpr int SM_W = 0;
 constexpr int SM_ACT = SM_W + W_STAGES * W_STAGE_BYTES;
 constexpr int SM_RAW = SM_ACT + 2 * ACT_BUF_BYTES;
 constexpr int SM_COEF = SM_RAW + RAW_STAGES * RAW_BYTES;
-constexpr int COEF_BYTES = 3 * CB * 4;          // (a, b, alpha) of the block's 16 channels travel with the raw block (cp.async)
-constexpr int SM_EPI = SM_COEF + 1024;
+constexpr int SM_EPI = SM_COEF + 4 * CIN_PAD_MAX * 4;   // per-channel prologue coefficients of the current utterance (4 x 1120 floats)
 constexpr int SM_BAR = SM_EPI + 8 * (32 * TPITCH + 32) * 4;
 constexpr int SM_TOTAL = SM_BAR + 512;
-static_assert(RAW_STAGES * COEF_BYTES <= 1024, "coefficient ring");
 static_assert(SM_TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 
 // barrier slots (8 B each) inside SM_BAR
@@ -244,6 +242,39 @@ __device__ __forceinline__ void epi_rows(float* T, const float* bsm, float* yp, 
         if (STATS) T[r * TPITCH + lane] = val;
       }
     }
+  }
+}
+
+// Vector variant for 16-byte aligned rows (row lengths multiples of 4 floats, unit output stride): lane -> (sub-row
+// lane / 8, column group lane % 8); pass p handles rows 4p .. 4p+3, each lane four consecutive columns: 128-bit shared
+// loads, 128-bit global loads / stores (a warp instruction moves four fully used 128-byte row segments) -- a quarter of
+// the memory instructions of the scalar path.  rv[4p + e] = residual of (row 4p + lane/8, column 4*(lane%8) + e).
+template <bool RES, int ACC, bool STATS>
+__device__ __forceinline__ void epi_rows_vec(float* T, const float* bsm, float* ybase, const float (&rv)[32], unsigned ys, int lane,
+                                             float out_div, float acc_div) {
+  const int sr = lane >> 3, cg = lane & 7;
+  float4 yo[8];
+  if (ACC) {
+#pragma unroll
+    for (int p = 0; p < 8; ++p) yo[p] = *reinterpret_cast<const float4*>(ybase + (unsigned)(4 * p + sr) * ys + 4 * cg);
+  }
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int r = 4 * p + sr;
+    float4 t4 = *reinterpret_cast<const float4*>(&T[r * TPITCH + 4 * cg]);
+    const float bb = bsm[r];
+    float val[4] = {t4.x + bb, t4.y + bb, t4.z + bb, t4.w + bb};
+    const float yv[4] = {ACC ? yo[p].x : 0.f, ACC ? yo[p].y : 0.f, ACC ? yo[p].z : 0.f, ACC ? yo[p].w : 0.f};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (RES) val[e] += rv[4 * p + e];
+      if (out_div != 1.0f) val[e] = __fdiv_rn(val[e], out_div);
+      if (ACC == 1) val[e] = yv[e] + val[e];
+      if (ACC == 2) val[e] = __fdiv_rn(yv[e] + val[e], acc_div);
+    }
+    const float4 o4 = make_float4(val[0], val[1], val[2], val[3]);
+    *reinterpret_cast<float4*>(ybase + (unsigned)r * ys + 4 * cg) = o4;
+    if (STATS) *reinterpret_cast<float4*>(&T[r * TPITCH + 4 * cg]) = o4;
   }
 }
 
@@ -437,6 +468,8 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     const int Lin_ = a.Lin, pre_act_ = a.pre_act, Cin_ = a.Cin;
     const float slope_ = a.pre_slope;
     const bool has_affine = a.pre_a != nullptr, is_snake = pre_act_ == ST2_ACT_SNAKE;
+    float* coef = reinterpret_cast<float*>(smem + SM_COEF);
+    const int cin_pad = ncb * CB;
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int total_blocks = my_tiles * ncb;
     const unsigned long long xaddr4 = (unsigned long long)(uintptr_t)a.x >> 2;
@@ -444,7 +477,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     const float* x_al = reinterpret_cast<const float*>((uintptr_t)a.x & ~(uintptr_t)15);
     // issue mapping: thread -> one channel of the block (st / 20) and every 20th 16-byte chunk of its row
     const int ich = st / 20, iq0 = st - ich * 20;
-    int i_tile = -1, i_g0 = 0, i_b = 0;  // producer-side tile state (runs RAW_STAGES-1 blocks ahead of the conversion)
+    int i_tile = -1, i_g0 = 0;  // producer-side tile state (runs RAW_STAGES-1 blocks ahead of the conversion)
     long long i_boff = 0;
     const int dbg_i = g_dbg;
     auto issue = [&](int g) {
@@ -453,18 +486,10 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
         if (tl != i_tile) {
           i_tile = tl;
           const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
-          i_b = tc_.b;
           i_boff = (long long)tc_.b * a.x_bstride;
           i_g0 = tc_.tq * TN - a.pad;
         }
         const int c = cb * CB + ich;
-        if (iq0 < 3) {
-          // this channel's AdaIN scale / shift / Snake alpha ride along with the raw block (zero-filled when absent)
-          const uint32_t cdst = sbase + SM_COEF + (g % RAW_STAGES) * COEF_BYTES + (uint32_t)(iq0 * CB + ich) * 4;
-          const bool cok = (c < Cin_) && (iq0 < 2 ? has_affine : is_snake);
-          const float* csrc = iq0 == 0 ? a.pre_a + (long long)i_b * Cin_ + c : (iq0 == 1 ? a.pre_b + (long long)i_b * Cin_ + c : a.pre_alpha + c);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(cdst), "l"(cok ? csrc : a.x), "r"(cok ? 4 : 0) : "memory");
-        }
         const long long e0 = i_boff + (long long)min(c, Cin_ - 1) * Lin_ + i_g0;   // first window element, floats from a.x
         const int shift = (int)((xaddr4 + (unsigned long long)e0) & 3ull);
         const int rlo = max(0, -i_g0), rhi = min(RW, Lin_ - i_g0);              // rows [rlo, rhi) are inside the tensor
@@ -488,7 +513,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     };
     for (int g = 0; g < RAW_STAGES - 1; ++g) issue(g);
     int as = 0, aph = 0;
-    int c_tile = -1, c_g0 = 0;
+    int c_tile = -1, c_g0 = 0, c_b = 0, last_b = -1;
     long long c_boff = 0;
     // conversion mapping: warp parity -> K chunk, (warp / 2, lane) -> 160 rows per pass: every shared-memory access of
     // a warp touches consecutive words / consecutive 16-byte rows
@@ -502,29 +527,38 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       if (tl != c_tile) {
         c_tile = tl;
         const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
+        c_b = tc_.b;
         c_boff = (long long)tc_.b * a.x_bstride;
         c_g0 = tc_.tq * TN - a.pad;
       }
       asm volatile("cp.async.wait_group %0;" ::"n"(RAW_STAGES - 2) : "memory");
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));  // block g landed for everybody; block g-1 fully converted
       issue(g + RAW_STAGES - 1);                             // reuses the slot of block g-1
+      if (c_b != last_b) {
+        // per-channel prologue coefficients of this utterance, with the 2^6 operand scale folded in: z' = 64 z = (64a) x + 64b;
+        // snake(z) * 64 = z' + (64/alpha) sin^2((alpha/64) z'); LeakyReLU is positively homogeneous
+        for (int c = st; c < cin_pad; c += NUM_STAGERS) {
+          float pa = 0.f, pb = 0.f, al = 1.f;  // padded channels stage exact zeros
+          if (c < Cin_) {
+            pa = 1.f;
+            if (has_affine) { pa = a.pre_a[c_b * Cin_ + c]; pb = a.pre_b[c_b * Cin_ + c]; }
+            if (is_snake) al = a.pre_alpha[c];
+          }
+          coef[c] = pa * xs_; coef[CIN_PAD_MAX + c] = pb * xs_; coef[2 * CIN_PAD_MAX + c] = al * (1.0f / X_SCALE);
+          coef[3 * CIN_PAD_MAX + c] = xs_ / al;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(NUM_STAGERS));
+        last_b = c_b;
+      }
       const int c0 = cb * CB + kc * 8;
       float pa[8], pb[8], al[8], ia[8];
       int sh[8];
       {
-        // the 2^6 operand scale is folded into the coefficients: z' = 64 z = (64a) x + 64b; snake(z) * 64 =
-        // z' + (64/alpha) sin^2((alpha/64) z'); LeakyReLU is positively homogeneous
-        const float* cf = reinterpret_cast<const float*>(smem + SM_COEF + (g % RAW_STAGES) * COEF_BYTES) + kc * 8;
         const int sh0 = (int)((xaddr4 + (unsigned long long)(c_boff + (long long)c0 * Lin_ + c_g0)) & 3ull), lin3 = Lin_ & 3;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const bool cv = (c0 + j) < Cin_;
-          const float a_ = (has_affine || !cv) ? cf[j] : 1.0f;          // padded channels: 0 (their raw rows are zero-filled too)
-          const float al_ = (is_snake && cv) ? cf[2 * CB + j] : 1.0f;
-          pa[j] = a_ * xs_;
-          pb[j] = cf[CB + j] * xs_;
-          al[j] = al_ * (1.0f / X_SCALE);
-          ia[j] = __frcp_rn(al_) * xs_;
+          pa[j] = coef[c0 + j]; pb[j] = coef[CIN_PAD_MAX + c0 + j]; al[j] = coef[2 * CIN_PAD_MAX + c0 + j];
+          ia[j] = coef[3 * CIN_PAD_MAX + c0 + j];
           sh[j] = ((sh0 + j * lin3) & 3) + j * RAW_PITCH;   // 4-byte phase of channel c0+j's row start (padded channels: any)
         }
       }
@@ -563,6 +597,10 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     const float out_div_ = a.out_div, acc_div_ = a.accum_div;
     const bool has_stats = a.stats != nullptr;
     const bool dbg_noio = (g_dbg & 2) != 0;
+    // 128-bit epilogue path: every row of y / res starts 16-byte aligned and outputs are contiguous
+    const bool vec_ok = (ytst_ == 1) && (rshift_ == 0) && ((ytoff_ & 3) == 0) && ((y_len_ & 3) == 0) && ((a.y_bstride & 3) == 0) &&
+                        ((reinterpret_cast<size_t>(a.y) & 15) == 0) && (out_act_ == ST2_ACT_NONE) && (a.dup_q0_to < 0) &&
+                        (!a.res || (((res_len_ & 3) == 0) && ((a.res_bstride & 3) == 0) && ((reinterpret_cast<size_t>(a.res) & 15) == 0)));
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
@@ -603,7 +641,14 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
         const bool okc = (c0 + lane) < ncols;
         const float* rp0 = rb ? rb + ((tcol * ytst_ + ytoff_) >> rshift_) : nullptr;
         const unsigned rl = (unsigned)res_len_;
-        if (rb && rmax == 32 && (c0 + 32) <= ncols && !dbg_noio) {
+        if (rb && vec_ok && rmax == 32 && (c0 + 32) <= ncols && !dbg_noio) {
+          const float* rq = rb + (t0 + c0 + ytoff_) + 4 * (lane & 7);
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rq + (unsigned)(4 * p + (lane >> 3)) * rl));
+            rv[4 * p] = r4.x; rv[4 * p + 1] = r4.y; rv[4 * p + 2] = r4.z; rv[4 * p + 3] = r4.w;
+          }
+        } else if (rb && rmax == 32 && (c0 + 32) <= ncols && !dbg_noio) {
 #pragma unroll
           for (int r = 0; r < 32; ++r) rv[r] = __ldg(rp0 + (unsigned)r * rl);
         } else {
@@ -652,7 +697,8 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
           (void)rp; (void)rs;
           if (out_act_ == ST2_ACT_NONE) {
 #define EPI_(RES_, ACC_, ST_, F_) epi_rows<RES_, ACC_, ST_, F_>(T, bsm, yp, rv, ys, rmax, tv, lane, out_div_, acc_div_)
-#define EPI(RES_, ACC_, ST_) do { if (full) EPI_(RES_, ACC_, ST_, true); else EPI_(RES_, ACC_, ST_, false); } while (0)
+#define EPI(RES_, ACC_, ST_) do { if (full && vec_ok) epi_rows_vec<RES_, ACC_, ST_>(T, bsm, yb + (t0 + c0 + ytoff_), rv, (unsigned)ys, lane, out_div_, acc_div_); \
+                                 else if (full) EPI_(RES_, ACC_, ST_, true); else EPI_(RES_, ACC_, ST_, false); } while (0)
             const bool full = (rmax == 32) && (ncols - c0 >= 32);
             if (has_stats) {
               if (rb) { if (acc_ == 0) EPI(true, 0, true); else if (acc_ == 1) EPI(true, 1, true); else EPI(true, 2, true); }

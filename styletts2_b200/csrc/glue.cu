@@ -90,6 +90,27 @@ __global__ void expand_rows_kernel(const float* __restrict__ src, long long src_
   for (int c = threadIdx.x; c < C; c += blockDim.x) dr[c] = sr[c];
 }
 
+// Strided Conv1d (stride S, K = J*S taps) as a stride-1 conv over the polyphase view of its input:
+// xp[b, c*S + r, q] = x[b, c, q*S + r - pad] (zero outside), q < Lp.  A block reads S*128 CONSECUTIVE samples of one input
+// row (coalesced), redistributes them through shared memory and writes S rows of 128 consecutive outputs.
+__global__ void __launch_bounds__(128) polyphase_gather_kernel(const float* __restrict__ x, long long x_bstride, int C, int L, int S, int pad,
+                                                               int Lp, float* __restrict__ xp) {
+  extern __shared__ float seg[];   // S * 128
+  const int b = blockIdx.z, c = blockIdx.y, q0 = blockIdx.x * 128;
+  const float* xr = x + (long long)b * x_bstride + (long long)c * L;
+  const int base = q0 * S - pad;
+  for (int i = threadIdx.x; i < S * 128; i += 128) {
+    const int t = base + i;
+    seg[i] = (t >= 0 && t < L) ? xr[t] : 0.f;
+  }
+  __syncthreads();
+  const int q = q0 + threadIdx.x;
+  if (q < Lp) {
+    float* o = xp + ((long long)b * C * S + (long long)c * S) * Lp + q;
+    for (int r = 0; r < S; ++r) o[(long long)r * Lp] = seg[threadIdx.x * S + r];
+  }
+}
+
 __global__ void expand_cl_kernel(const float* __restrict__ src, const int* __restrict__ tok, int C, int N, int T,
                                  float* __restrict__ out, long long out_bstride) {
   const int b = blockIdx.z, c = blockIdx.y;
@@ -199,6 +220,14 @@ int st2_expand_rows(const float* src, long long src_ld, const int* tok, int B, i
   expand_rows_kernel<<<dim3(T, B), 128, 0, (cudaStream_t)stream>>>(src, src_ld, tok, N, T, C, out, out_ld);
   ++g_launches;
   ST2_CHECK_LAUNCH("st2_expand_rows");
+  return 0;
+}
+
+int st2_polyphase_gather(const float* x, long long x_bstride, int B, int C, int L, int S, int pad, int Lp, float* xp, void* stream) {
+  ST2_REQUIRE(x && xp && B > 0 && C > 0 && L > 0 && S > 0 && S <= 64 && Lp > 0, "st2_polyphase_gather", "bad args");
+  polyphase_gather_kernel<<<dim3(cdiv(Lp, 128), C, B), 128, S * 128 * sizeof(float), (cudaStream_t)stream>>>(x, x_bstride, C, L, S, pad, Lp, xp);
+  ++g_launches;
+  ST2_CHECK_LAUNCH("st2_polyphase_gather");
   return 0;
 }
 

@@ -107,6 +107,7 @@ SIGNATURES = {
     "st2_frame_tokens": [_vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "st2_expand_rows": [_vp, _ll, _vp, _i, _i, _i, _i, _vp, _ll, _vp],
     "st2_expand_cl": [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp],
+    "st2_polyphase_gather": [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp],
     "st2_sine_source": [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, C.c_ulonglong, C.c_ulonglong, _vp, _vp],
     "st2_randn": [_vp, _ll, C.c_ulonglong, C.c_ulonglong, _vp, _vp],
     "st2_rng_advance": [_vp, _vp],

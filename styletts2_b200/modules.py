@@ -98,13 +98,32 @@ class Conv1d(_Cached):
         self.bias = nn.Parameter(torch.zeros(cout))
 
     def _prepare(self):
-        return ops.conv_weight_layout(self.weight), _maybe_wtc(self.weight.detach(), self.stride, 1, getattr(self, "tc_mode", TC_FAST))
+        wt, wtc = ops.conv_weight_layout(self.weight), _maybe_wtc(self.weight.detach(), self.stride, 1, getattr(self, "tc_mode", TC_FAST))
+        poly = None
+        S, k = self.stride, self.k
+        if S > 1 and k % S == 0 and self.cin * S >= 16 and self.cout >= 16 and ops.USE_TC and self.weight.is_cuda:
+            # strided conv as a stride-1 conv over the polyphase input (ops.polyphase_gather): wp[co, c*S + r, j] = w[co, c, j*S + r]
+            J = k // S
+            wp = self.weight.detach().view(self.cout, self.cin, J, S).permute(0, 1, 3, 2).reshape(self.cout, self.cin * S, J).contiguous()
+            if ops.conv_tc_supported(self.cin * S, self.cout, J, 1, 1):
+                poly = (ops.conv_weight_layout(wp), ops.conv_tc_weight_layout(wp, getattr(self, "tc_mode", TC_FAST)), J)
+        return wt, wtc, poly
 
     def wt(self):
         return self.prepared()[0]
 
     def wtc(self):
         return self.prepared()[1]
+
+    def run(self, x, want_stats=False):
+        """(y, stats) of the plain conv (no prologue); strided convs take the polyphase tensor-core route when prepared."""
+        wt, wtc, poly = self.prepared()
+        Lout = (x.shape[-1] + 2 * self.padding - self.k) // self.stride + 1
+        if poly is not None and self.cin * self.cout * self.k * Lout >= ops.TC_MIN_WORK:
+            wtp, wtcp, J = poly
+            xp = ops.polyphase_gather(x, self.stride, self.padding, Lout + J - 1)
+            return ops.conv1d(xp, wtp, self.bias, K=J, pad=0, want_stats=want_stats, wtc=wtcp)
+        return ops.conv1d(x, wt, self.bias, K=self.k, stride=self.stride, pad=self.padding, want_stats=want_stats, wtc=wtc)
 
     def forward(self, x, **kw):
         y, _ = ops.conv1d(x, self.wt(), self.bias, K=self.k, stride=self.stride, pad=self.padding, wtc=self.wtc(), **kw)
@@ -598,7 +617,7 @@ class Generator(nn.Module):
         nk = self.num_kernels
         for i in range(self.num_upsamples):
             nc, up = self.noise_convs[i], self.ups[i]
-            xs, xst = ops.conv1d(har, nc.wt(), nc.bias, K=nc.k, stride=nc.stride, pad=nc.padding, want_stats=True, wtc=nc.wtc())
+            xs, xst = nc.run(har, want_stats=True)
             xs, _ = self.noise_res[i].run(xs, fcs, xst)
             x, st = ops.conv_transpose1d(x, up.wp(), up.bias, K=up.k, stride=up.stride, padding=up.padding, pre_act=ACT_LRELU,
                                          slope=0.1, res=xs, reflect_left1=(i == self.num_upsamples - 1), want_stats=True,
@@ -644,7 +663,7 @@ class HifiGenerator(nn.Module):
         nk = self.num_kernels
         for i in range(self.num_upsamples):
             nc, up = self.noise_convs[i], self.ups[i]
-            xs, xst = ops.conv1d(har, nc.wt(), nc.bias, K=nc.k, stride=nc.stride, pad=nc.padding, want_stats=True, wtc=nc.wtc())
+            xs, xst = nc.run(har, want_stats=True)
             xs, _ = self.noise_res[i].run(xs, fcs, xst)
             x, st = ops.conv_transpose1d(x, up.wp(), up.bias, K=up.k, stride=up.stride, padding=up.padding, pre_act=ACT_SNAKE,
                                          alpha=self.alphas[i], res=xs, want_stats=True, wtc=up.wtc())

@@ -191,6 +191,16 @@ def conv1d(x, wt, bias=None, *, K, stride=1, dil=1, pad=0, pre=None, pre_act=ACT
     return out, stats
 
 
+def polyphase_gather(x, S: int, pad: int, Lp: int) -> torch.Tensor:
+    """x [B,C,L] -> xp [B, C*S, Lp], xp[b, c*S + r, q] = x[b, c, q*S + r - pad] (zero outside)"""
+    x = _cl(x)
+    B, Cc, Ln = x.shape
+    xp = empty(B, Cc * S, Lp, device=x.device)
+    with _prof(f"polyphase_gather c{Cc} L{Ln} s{S} B{B}", 0.0, 4.0 * B * Cc * (Ln + S * Lp)):
+        L.call("st2_polyphase_gather", ptr(x), x.stride(0), B, Cc, Ln, S, pad, Lp, ptr(xp), stream_ptr())
+    return xp
+
+
 def convT_tc_weight_layout(w: torch.Tensor, stride: int, padding: int, mode: int = TC_FAST) -> TCWeights:
     """folded fp32 ConvTranspose1d weight [Cin,Cout,K] -> per-phase tensor-core blocks"""
     w = w.detach().contiguous()
