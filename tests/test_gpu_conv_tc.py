@@ -192,3 +192,27 @@ def test_linear_tc_range_guard_reports_fp16_plane_overflow():
     with pytest.raises(FloatingPointError):
         ops.check_range()
     ops.check_range()                                   # the fetch cleared the flag
+
+
+@pytest.mark.parametrize("cin,cout,k,s,L", [(22, 256, 12, 6, 6001), (1, 128, 60, 30, 9000), (22, 64, 12, 6, 1205)])
+def test_strided_noise_conv_polyphase_route_matches_fp32(cin, cout, k, s, L):
+    """noise_convs of the generators (kernel 2*stride): the polyphase rewrite onto the tensor-core kernel == F.conv1d."""
+    from styletts2_b200 import ops
+    from styletts2_b200.modules import Conv1d
+    m = Conv1d(cin, cout, k, stride=s, padding=(s + 1) // 2).to(D)
+    x = rnd(2, cin, L, seed=1)
+    ref = F.conv1d(x.double(), m.weight.detach().cpu().double(), m.bias.detach().cpu().double(), stride=s, padding=(s + 1) // 2).float()
+    ops.PROFILE = []
+    try:
+        y, st = m.run(x.to(D), want_stats=True)
+        torch.cuda.synchronize()
+        names = [p[0] for p in ops.PROFILE]
+    finally:
+        ops.PROFILE = None
+    assert y.shape == ref.shape
+    assert any(n.startswith("polyphase_gather") for n in names) and any(n.startswith("conv1d_tc") for n in names), names
+    r = maxdiff(y, ref) / float(ref.abs().max())
+    assert r < TOL[0], r
+    ca, cb = ops.adain_coef(st, torch.zeros(2, 2 * cout, device=D))
+    ea = 1 / torch.sqrt(ref.var(-1, unbiased=False) + 1e-5)
+    assert maxdiff(ca, ea) / float(ea.abs().max()) < 1e-4
