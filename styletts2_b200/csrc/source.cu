@@ -208,8 +208,13 @@ __global__ void __launch_bounds__(320) istft20_kernel(const float* __restrict__ 
   // frames that can touch those samples: n = n'+10, f in [ceil((n-19)/5), floor(n/5)] -> [fb0-1, fb0+ISTFT_FB+1]
   const int fbase = fb0 - 1;
   const float* xb = x + (long long)b * 22 * Fr;
+  // the twiddle / window tables are indexed by (k*m) % 20 with m different in every lane: constant memory would serialise
+  // those reads, shared memory serves them in one pass
+  __shared__ float cs_s[20], sn_s[20], win_s[20];
+  if (threadIdx.x < 20) { cs_s[threadIdx.x] = c_tab.cs[threadIdx.x]; sn_s[threadIdx.x] = c_tab.sn[threadIdx.x]; win_s[threadIdx.x] = c_tab.win[threadIdx.x]; }
+  // bin-major walk: consecutive threads read consecutive frames of ONE bin row (coalesced)
   for (int i = threadIdx.x; i < (ISTFT_FB + 4) * 11; i += blockDim.x) {
-    const int fl = i / 11, k = i - fl * 11;
+    const int k = i / (ISTFT_FB + 4), fl = i - k * (ISTFT_FB + 4);
     const int f = fbase + fl;
     float re = 0.f, im = 0.f;
     if (f >= 0 && f < Fr) {
@@ -240,10 +245,10 @@ __global__ void __launch_bounds__(320) istft20_kernel(const float* __restrict__ 
 #pragma unroll
     for (int k = 1; k <= 9; ++k) {
       const int idx = (k * m) % 20;
-      v = fmaf(2.0f * re_s[fl][k], c_tab.cs[idx], v);
-      v = fmaf(-2.0f * im_s[fl][k], c_tab.sn[idx], v);
+      v = fmaf(2.0f * re_s[fl][k], cs_s[idx], v);
+      v = fmaf(-2.0f * im_s[fl][k], sn_s[idx], v);
     }
-    const float w = c_tab.win[m];
+    const float w = win_s[m];
     acc = fmaf(v * 0.05f, w, acc);
     env = fmaf(w, w, env);
   }
