@@ -69,7 +69,9 @@ constexpr int RAW_PITCH = 320;                  // floats per channel row of a r
 constexpr int RAW_CHUNKS = RAW_PITCH / 4;
 constexpr int RAW_BYTES = CB * RAW_PITCH * 4;   // 20 KB
 constexpr int CIN_PAD_MAX = 1120;
-constexpr int NUM_STAGERS = 320;                // 10 warps
+constexpr int NUM_STAGERS = 320;                // 10 warps (8 would not buy registers: allocation is per 4 warps, 18 -> 20)
+constexpr int ST_PER_CH = NUM_STAGERS / CB;     // issue mapping: threads per channel row of a raw block
+constexpr int ROWS_PER_PASS = (NUM_STAGERS / 64) * 32;  // conversion mapping: rows covered per pass
 constexpr int NUM_EPI = 256;                    // 8 warps: two per TMEM lane quarter (each takes half of the columns)
 constexpr int THREADS = 64 + NUM_STAGERS + NUM_EPI;  // 640 = 20 warps (register allocation granularity: 4 warps)
 constexpr int TPITCH = 36;                      // epilogue transpose row pitch (floats), 16-byte aligned rows
@@ -86,6 +88,7 @@ constexpr int SM_COEF = SM_RAW + RAW_STAGES * RAW_BYTES;
 constexpr int SM_EPI = SM_COEF + 4 * CIN_PAD_MAX * 4;   // per-channel prologue coefficients of the current utterance (4 x 1120 floats)
 constexpr int SM_BAR = SM_EPI + 8 * (32 * TPITCH + 32) * 4;
 constexpr int SM_TOTAL = SM_BAR + 512;
+static_assert(RAW_CHUNKS % ST_PER_CH == 0 && NUM_STAGERS % 64 == 0, "stager mappings");
 static_assert(SM_TOTAL <= 232448, "shared memory budget (227 KB per CTA)");
 
 // barrier slots (8 B each) inside SM_BAR
@@ -475,8 +478,8 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     const unsigned long long xaddr4 = (unsigned long long)(uintptr_t)a.x >> 2;
     const long long tensor_end = (long long)(a.B - 1) * a.x_bstride + (long long)Cin_ * Lin_;  // floats from a.x
     const float* x_al = reinterpret_cast<const float*>((uintptr_t)a.x & ~(uintptr_t)15);
-    // issue mapping: thread -> one channel of the block (st / 20) and every 20th 16-byte chunk of its row
-    const int ich = st / 20, iq0 = st - ich * 20;
+    // issue mapping: thread -> one channel of the block and every ST_PER_CH-th 16-byte chunk of its row
+    const int ich = st / ST_PER_CH, iq0 = st - ich * ST_PER_CH;
     int i_tile = -1, i_g0 = 0;  // producer-side tile state (runs RAW_STAGES-1 blocks ahead of the conversion)
     long long i_boff = 0;
     const int dbg_i = g_dbg;
@@ -500,13 +503,13 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
         const long long end_rel = tensor_end - w0;
         uint32_t dst = sbase + SM_RAW + (g % RAW_STAGES) * RAW_BYTES + (uint32_t)(ich * RAW_PITCH + iq0 * 4) * 4;
 #pragma unroll
-        for (int i = 0; i < RAW_CHUNKS / 20; ++i) {
-          const int q = iq0 + 20 * i;
+        for (int i = 0; i < RAW_CHUNKS / ST_PER_CH; ++i) {
+          const int q = iq0 + ST_PER_CH * i;
           const bool ok = (q >= qlo) && (q < qhi);
           const long long rem = end_rel - 4ll * q;
           const int nbytes = ok ? (rem >= 4 ? 16 : (int)rem * 4) : 0;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src0 + 4 * q : x_al), "r"(nbytes) : "memory");
-          dst += 20 * 16;
+          dst += ST_PER_CH * 16;
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -515,12 +518,12 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     int as = 0, aph = 0;
     int c_tile = -1, c_g0 = 0, c_b = 0, last_b = -1;
     long long c_boff = 0;
-    // conversion mapping: warp parity -> K chunk, (warp / 2, lane) -> 160 rows per pass: every shared-memory access of
+    // conversion mapping: warp parity -> K chunk, (warp / 2, lane) -> ROWS_PER_PASS rows per pass: every shared-memory access of
     // a warp touches consecutive words / consecutive 16-byte rows
     const int sw = warp - 2;
     const int dbg_st = g_dbg;
     const int kc = sw & 1, rg = (sw >> 1) * 32 + lane;
-    constexpr int NRC = (RW_MAX + 159) / 160;
+    constexpr int NRC = (RW_MAX + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
     const float xs_ = X_SCALE;
     for (int g = 0; g < total_blocks; ++g) {
       const int tl = g / ncb, cb = g - tl * ncb;
@@ -568,7 +571,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       uint8_t* p1 = p0 + ACT_PLANE_BYTES;
 #pragma unroll
       for (int i = 0; i < NRC; ++i) {
-        const int r = rg + 160 * i;
+        const int r = rg + ROWS_PER_PASS * i;
         if (r < RW && !(dbg_st & 4)) {
           const int gt = c_g0 + r;
           const bool inb = (gt >= 0) && (gt < Lin_);
