@@ -616,21 +616,34 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       bsm[lane] = (a.bias && lane < rmax) ? a.bias[co_base + lane] : 0.f;
       float* yb = a.y + (long long)tc_.b * a.y_bstride + (long long)co_base * y_len_;
       const float* rb = a.res ? a.res + (long long)tc_.b * a.res_bstride + (long long)co_base * res_len_ : nullptr;
-      if (ytst_ == 1 && lane < rmax && !dbg_noio) {
-        // While the MMAs of this tile run: pull this warp's residual rows (and, when accumulating, the previous output)
-        // into L2, so that the register loads of the epilogue see L2 latency instead of HBM latency.  Lane = row; each of
-        // the four 128-byte row segments may straddle two lines (rows start at any 4-byte phase).
+      if (ytst_ == 1 && !dbg_noio && (rb || acc_)) {
+        // Pull the residual rows (and, when accumulating, the previous output) of this warp's part of its NEXT tile into
+        // L2 now: a whole tile of lead time (the epilogue-bound launches have none within a tile), so that the register
+        // loads of the next epilogue see L2 latency instead of HBM latency -- the epilogue can hold only 32 KB of loads in
+        // flight per SM.  Lane = row; each 128-byte row segment may straddle two lines (rows start at any 4-byte phase).
+        // The very first tile of a CTA prefetches for itself.
+        const int ntile = (it == 0) ? tile : tile + (int)gridDim.x;
+        for (int rep = 0; rep < ((it == 0) ? 2 : 1); ++rep) {
+          const int pt = (rep == 0) ? ntile : tile + (int)gridDim.x;
+          if (pt < ntiles) {
+            const TileCoord nc_ = tile_coord(pt, n_tq, n_cob);
+            const int nrq = rows_per_quarter(Cout_, nc_.cob);
+            const int nco = nc_.cob * TM + ew * nrq;
+            if (lane < min(nrq, Cout_ - nco)) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int cq = t0 + half * (TN / 2) + 32 * q;
-          if (cq < Lq_) {
-            if (rb) {
-              const float* rp = rb + (long long)lane * res_len_ + ((cq + ytoff_) >> rshift_);
-              prefetch_l2(rp); prefetch_l2(rp + 31);
-            }
-            if (acc_) {
-              const float* yq = yb + (long long)lane * y_len_ + cq + ytoff_;
-              prefetch_l2(yq); prefetch_l2(yq + 31);
+              for (int q = 0; q < 4; ++q) {
+                const int cq = nc_.tq * TN + half * (TN / 2) + 32 * q;
+                if (cq < Lq_) {
+                  if (rb) {
+                    const float* rp = a.res + (long long)nc_.b * a.res_bstride + (long long)(nco + lane) * res_len_ + ((cq + ytoff_) >> rshift_);
+                    prefetch_l2(rp); prefetch_l2(rp + 31);
+                  }
+                  if (acc_) {
+                    const float* yq = a.y + (long long)nc_.b * a.y_bstride + (long long)(nco + lane) * y_len_ + cq + ytoff_;
+                    prefetch_l2(yq); prefetch_l2(yq + 31);
+                  }
+                }
+              }
             }
           }
         }

@@ -50,7 +50,11 @@ def init_from_env(backend: str = "nccl"):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not torch.distributed.is_initialized():
-        torch.distributed.init_process_group(backend=backend)
+        kw = {}
+        if backend == "nccl" and torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)     # bind the communicator to this rank's GPU (no device guessing)
+        torch.distributed.init_process_group(backend=backend, **kw)
     return rank, local, world
 
 
