@@ -281,8 +281,6 @@ __device__ __forceinline__ void epi_rows_vec(float* T, const float* bsm, float* 
   }
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int ncb, const int RW, const int ntiles,
@@ -323,7 +321,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     // MMAs and commits; every quantity is warp-uniform, descriptors are (low, high) words and a tap only bumps the low
     // word.  [A single lane walking the generic loop below spends ~250 cycles of dependent instructions per tap -- as
     // long as the two MMAs of a tap take on the tensor pipe (profiles/r02_tc_bench_*.txt).]
-    if (g_dbg == 0 && !(g_trace != nullptr && blockIdx.x == 0)) {
+    if ((g_dbg & (1 | 8)) == 0 && !(g_trace != nullptr && blockIdx.x == 0)) {
       const uint32_t idesc = make_idesc();
       const uint32_t elected = elect_one();
       const uint64_t da_d = make_desc(sbase + SM_W, TM * 16, 128), db_d = make_desc(sbase + SM_ACT, (uint32_t)RWP * 16, 128);
@@ -616,38 +614,8 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
       bsm[lane] = (a.bias && lane < rmax) ? a.bias[co_base + lane] : 0.f;
       float* yb = a.y + (long long)tc_.b * a.y_bstride + (long long)co_base * y_len_;
       const float* rb = a.res ? a.res + (long long)tc_.b * a.res_bstride + (long long)co_base * res_len_ : nullptr;
-      if (ytst_ == 1 && !dbg_noio && (rb || acc_)) {
-        // Pull the residual rows (and, when accumulating, the previous output) of this warp's part of its NEXT tile into
-        // L2 now: a whole tile of lead time (the epilogue-bound launches have none within a tile), so that the register
-        // loads of the next epilogue see L2 latency instead of HBM latency -- the epilogue can hold only 32 KB of loads in
-        // flight per SM.  Lane = row; each 128-byte row segment may straddle two lines (rows start at any 4-byte phase).
-        // The very first tile of a CTA prefetches for itself.
-        const int ntile = (it == 0) ? tile : tile + (int)gridDim.x;
-        for (int rep = 0; rep < ((it == 0) ? 2 : 1); ++rep) {
-          const int pt = (rep == 0) ? ntile : tile + (int)gridDim.x;
-          if (pt < ntiles) {
-            const TileCoord nc_ = tile_coord(pt, n_tq, n_cob);
-            const int nrq = rows_per_quarter(Cout_, nc_.cob);
-            const int nco = nc_.cob * TM + ew * nrq;
-            if (lane < min(nrq, Cout_ - nco)) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int cq = nc_.tq * TN + half * (TN / 2) + 32 * q;
-                if (cq < Lq_) {
-                  if (rb) {
-                    const float* rp = a.res + (long long)nc_.b * a.res_bstride + (long long)(nco + lane) * res_len_ + ((cq + ytoff_) >> rshift_);
-                    prefetch_l2(rp); prefetch_l2(rp + 31);
-                  }
-                  if (acc_) {
-                    const float* yq = a.y + (long long)nc_.b * a.y_bstride + (long long)(nco + lane) * y_len_ + cq + ytoff_;
-                    prefetch_l2(yq); prefetch_l2(yq + 31);
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
+      // (L2 prefetches of the residual rows -- for this tile or one tile ahead -- were measured neutral / 12 % slower: the
+      // extra requests compete with the loads they are meant to help; profiles/r02_tc_bench_*.txt)
       // Residual values of one 32x32 block: lane = column, rv[r] = row r.  The loads of block c+1 are issued right after
       // the row loop of block c has consumed rv (same registers): their latency hides behind the statistics of block c
       // and the TMEM load / transpose of block c+1; the first block's loads fly during the wait for the accumulator.

@@ -71,6 +71,9 @@ if __name__ == "__main__":
             variants = ((1, "f16-2nd"), (2, "no-epi-io"), (4, "no-convert"), (8, "no-mma"), (2 | 4, "no-io+no-conv"), (2 | 4 | 8, "skeleton"))
             if os.environ.get("TC_BENCH_QUICK"):
                 variants = ()
+            if os.environ.get("TC_BENCH_MMA"):      # production issue path with the other roles switched off one by one
+                variants = ((4, "no-convert"), (2, "no-epi-io"), (64, "no-epi"), (2 | 4, "no-io+no-conv"), (4 | 64, "no-conv+no-epi"),
+                            (4 | 16 | 32 | 64, "mma+handshake only"), (4 | 32 | 64, "mma+weights only"))
             if mode == 0 and os.environ.get("TC_BENCH_DEEP"):
                 variants = ((2 | 4 | 8, "skeleton"), (2 | 4 | 8 | 16, "skel-noW"), (2 | 4 | 8 | 32, "skel-noRaw"), (2 | 4 | 8 | 16 | 32, "skel-handshake"),
                             (4 | 8 | 16 | 32 | 64, "handshake-noEpi"), (16, "full-noW"), (64, "full-noEpi"), (16 | 64, "full-noW-noEpi"), (32, "full-noRaw"),
@@ -82,5 +85,5 @@ if __name__ == "__main__":
                 row.append(f"{fn} {timeit(call):.3f}")
             lib.call("st2_debug_set_flags", 0)
             print("  " + " | ".join(row))
-            if mode == 0:
+            if mode == 0 and not os.environ.get("TC_BENCH_MMA"):
                 trace(call, name)
