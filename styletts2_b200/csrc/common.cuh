@@ -70,4 +70,22 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// One-time host-side setup (cudaFuncSetAttribute, __constant__ tables, device queries) is PER DEVICE: a process that
+// drives several GPUs must repeat it on each.  Usage: static PerDevice once; if (once.first()) { ...setup for current device... }
+struct PerDevice {
+  bool done[64] = {false};
+  int value[64] = {0};
+  int dev() const {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+  }
+  bool first() {
+    const int d = dev();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 }  // namespace st2

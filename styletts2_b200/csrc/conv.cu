@@ -196,12 +196,11 @@ static int conv_launch(const st2_conv_args& a, cudaStream_t st) {
     return (int)cudaErrorInvalidValue;
   }
   dim3 grid(cdiv(a.Lq, TQ), cdiv(a.Cout, co_t), a.B);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDevice once;
+  if (once.first()) {
     cudaFuncSetAttribute(conv1d_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv1d_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(conv1d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = true;
   }
   if (cow == 8) conv1d_kernel<8><<<grid, CONV_THREADS, smem, st>>>(a, ci_chunk, xt);
   else if (cow == 4) conv1d_kernel<4><<<grid, CONV_THREADS, smem, st>>>(a, ci_chunk, xt);

@@ -430,13 +430,13 @@ int st2_linear_tc_pre(const float* A, long long lda, const void* planes, const v
   a.M = M; a.Nf = Nf; a.K = K; a.act = act;
   const int n_tq = cdiv(M, ltc::TNT), n_cob = cdiv(Nf, ltc::TMF), ncb = cdiv(K, ltc::KB);
   const int ntiles = n_tq * n_cob;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  static PerDevice once;
+  if (once.first()) {
+    const int d = once.dev();
+    cudaDeviceGetAttribute(&once.value[d], cudaDevAttrMultiProcessorCount, d);
     cudaFuncSetAttribute(ltc::linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ltc::SM_TOTAL);
   }
+  const int num_sms = once.value[once.dev()];
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   ltc::linear_tc_kernel<<<grid, ltc::THREADS, ltc::SM_TOTAL, (cudaStream_t)stream>>>(a, ncb, ntiles, n_tq);
   ++g_launches;

@@ -494,21 +494,18 @@ extern "C" int st2_lstm_bidir(const float* gx, const float* whh, float* out, lon
   cudaError_t e = cudaMemsetAsync(work, 0, (3 * n + 64) * sizeof(float), st);
   if (e != cudaSuccess) { set_error("st2_lstm_bidir", e); return (int)e; }
   const size_t smem = (size_t)(4 * LSTM_UT + LSTM_BT) * (H + 4) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_done = true;
-  }
+  static PerDevice once_step;
+  if (once_step.first()) cudaFuncSetAttribute(lstm_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   ST2_REQUIRE(smem <= 160 * 1024, "st2_lstm_bidir", "hidden size too large");
   // persistent cooperative kernel when the grid fits on the device (H/4 * 2 CTAs), else one launch per step
-  static int coop = -1, num_sms = 0;
-  if (coop < 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  static PerDevice once_p, sms_p;
+  if (once_p.first()) {
+    const int d = once_p.dev();
+    cudaDeviceGetAttribute(&once_p.value[d], cudaDevAttrCooperativeLaunch, d);
+    cudaDeviceGetAttribute(&sms_p.value[d], cudaDevAttrMultiProcessorCount, d);
     cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   }
+  const int coop = once_p.value[once_p.dev()], num_sms = sms_p.value[once_p.dev()];
   if (coop && cdiv(H, LSTM_UT) * 2 <= num_sms) {
     dim3 pgrid(cdiv(H, LSTM_UT), 2);
     void* args[] = {(void*)&gx, (void*)&whh, (void*)&out, (void*)&o_bs, (void*)&o_ts, (void*)&o_cs, (void*)&lengths,

@@ -146,10 +146,10 @@ struct Tab20 {
   float sn[20];
 };
 __constant__ Tab20 c_tab;
-static bool g_tab_ready = false;
+static PerDevice g_tab_once;   // __constant__ memory is per device
 
 static int ensure_tab() {
-  if (g_tab_ready) return 0;
+  if (!g_tab_once.first()) return 0;
   Tab20 t;
   const double PI = 3.14159265358979323846;
   for (int m = 0; m < 20; ++m) {
@@ -160,8 +160,7 @@ static int ensure_tab() {
   // exact zeros / ones where the analytic value is exact
   t.cs[5] = 0.f; t.cs[15] = 0.f; t.sn[0] = 0.f; t.sn[10] = 0.f;
   cudaError_t e = cudaMemcpyToSymbol(c_tab, &t, sizeof(t));
-  if (e != cudaSuccess) { set_error("stft table", e); return (int)e; }
-  g_tab_ready = true;
+  if (e != cudaSuccess) { set_error("stft table", e); g_tab_once.done[g_tab_once.dev()] = false; return (int)e; }
   return 0;
 }
 
