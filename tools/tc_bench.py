@@ -58,7 +58,7 @@ def trace(call, label):
 
 if __name__ == "__main__":
     B = 8
-    shapes = [(B, 128, 11, 1, 61441, True), (B, 128, 3, 1, 61441, True), (B, 128, 3, 1, 61440, True), (B, 128, 7, 1, 61440, True), (B, 128, 7, 1, 61441, True), (4 * B, 256, 7, 1, 10240, True),
+    shapes = [(B, 128, 11, 1, 61441, True), (B, 128, 3, 1, 61441, True), (B, 128, 3, 1, 61441, False), (B, 128, 11, 1, 61441, False), (B, 128, 3, 1, 61440, True), (B, 128, 7, 1, 61440, True), (B, 128, 7, 1, 61441, True), (4 * B, 256, 7, 1, 10240, True),
               (4 * B, 256, 3, 1, 10240, True), (4 * B, 1024, 3, 1, 512, True), (4 * B, 1024, 1, 1, 512, False)]
     for (b, C, K, d, L, res) in shapes:
         fl = 2.0 * C * C * K * L * b
