@@ -281,6 +281,173 @@ __device__ __forceinline__ void epi_rows_vec(float* T, const float* bsm, float* 
   }
 }
 
+// Weight producer role (one lane of warp 1): one 1-D TMA bulk copy per pipeline stage = up to `tps` consecutive taps of one
+// 16-channel block (contiguous in the [cob][cb][tap] layout), `wstep` bytes per (16 channels, tap) step.
+__device__ __forceinline__ void weight_producer_role(const uint4* __restrict__ wtc, const uint32_t sbase, const uint32_t bar0,
+                                                     const int ncb, const int K, const int wstep, const int tps, const int ntiles,
+                                                     const int n_tq, const int n_cob) {
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int dbg_p = g_dbg;
+  int ws = 0, wph = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(wtc) + (size_t)tc_.cob * ncb * K * wstep;
+    for (int cb = 0; cb < ncb; ++cb) {
+      for (int tap0 = 0; tap0 < K; tap0 += tps) {
+        const uint32_t bytes = (uint32_t)(min(tps, K - tap0) * wstep);
+        mbar_wait(BAR(B_WEMPTY + ws), wph ^ 1);
+        if (dbg_p & 16) {
+          mbar_arrive(BAR(B_WFULL + ws));                    // timing experiment: no weight traffic
+        } else {
+          mbar_expect_tx(BAR(B_WFULL + ws), bytes);
+          bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, bytes, BAR(B_WFULL + ws));
+        }
+        src += bytes;
+        if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Activation stager role (warps 2 .. 2 + NUM_STAGERS/32 - 1), shared by the channel-major and the time-major kernel: both
+// read the staged window through the same K-major no-swizzle layout (one 16-byte row per frame and K chunk).
+template <int MODE>
+__device__ __forceinline__ void stager_role(const st2_conv_args& a, uint8_t* smem, const uint32_t sbase, const uint32_t bar0,
+                                            const int ncb, const int RW, const int ntiles, const int n_tq, const int n_cob,
+                                            const int tid, const int warp, const int lane) {
+  const int RWP = RW + 2;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  // ================================================================ activation stagers
+  // Raw fp32 frame windows travel HBM -> shared memory with 16-byte cp.async copies (no registers held while in
+  // flight): a ring of RAW_STAGES 16-channel blocks keeps ~60 KB per SM outstanding, which is what it takes to cover
+  // HBM latency.  Rows of the activation tensor start at any 4-byte phase (odd row lengths), so each channel row
+  // copies the 16-byte ALIGNED superset of its window; the phase (0..3 floats) is re-derived by the conversion.
+  // Chunks outside the tensor are zero-filled (src-size 0), the chunk that crosses the end of the tensor is
+  // trimmed; nothing before the 16-byte aligned start of the tensor's allocation is ever touched.
+  const int st = tid - 64;  // 0..319
+  const int Lin_ = a.Lin, pre_act_ = a.pre_act, Cin_ = a.Cin;
+  const float slope_ = a.pre_slope;
+  const bool has_affine = a.pre_a != nullptr, is_snake = pre_act_ == ST2_ACT_SNAKE;
+  float* coef = reinterpret_cast<float*>(smem + SM_COEF);
+  const int cin_pad = ncb * CB;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_blocks = my_tiles * ncb;
+  const unsigned long long xaddr4 = (unsigned long long)(uintptr_t)a.x >> 2;
+  const long long tensor_end = (long long)(a.B - 1) * a.x_bstride + (long long)Cin_ * Lin_;  // floats from a.x
+  const float* x_al = reinterpret_cast<const float*>((uintptr_t)a.x & ~(uintptr_t)15);
+  // issue mapping: thread -> one channel of the block and every ST_PER_CH-th 16-byte chunk of its row
+  const int ich = st / ST_PER_CH, iq0 = st - ich * ST_PER_CH;
+  int i_tile = -1, i_g0 = 0;  // producer-side tile state (runs RAW_STAGES-1 blocks ahead of the conversion)
+  long long i_boff = 0;
+  const int dbg_i = g_dbg;
+  auto issue = [&](int g) {
+    if (g < total_blocks && !(dbg_i & 32)) {
+      const int tl = g / ncb, cb = g - tl * ncb;
+      if (tl != i_tile) {
+        i_tile = tl;
+        const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
+        i_boff = (long long)tc_.b * a.x_bstride;
+        i_g0 = tc_.tq * TN - a.pad;
+      }
+      const int c = cb * CB + ich;
+      const long long e0 = i_boff + (long long)min(c, Cin_ - 1) * Lin_ + i_g0;   // first window element, floats from a.x
+      const int shift = (int)((xaddr4 + (unsigned long long)e0) & 3ull);
+      const int rlo = max(0, -i_g0), rhi = min(RW, Lin_ - i_g0);              // rows [rlo, rhi) are inside the tensor
+      int qlo = 0, qhi = 0;
+      if (c < Cin_ && rhi > rlo) { qlo = (rlo + shift) >> 2; qhi = (rhi + shift + 3) >> 2; }
+      const long long w0 = e0 - shift;                                          // aligned window start, floats from a.x
+      const float* src0 = a.x + w0;
+      const long long end_rel = tensor_end - w0;
+      uint32_t dst = sbase + SM_RAW + (g % RAW_STAGES) * RAW_BYTES + (uint32_t)(ich * RAW_PITCH + iq0 * 4) * 4;
+#pragma unroll
+      for (int i = 0; i < RAW_CHUNKS / ST_PER_CH; ++i) {
+        const int q = iq0 + ST_PER_CH * i;
+        const bool ok = (q >= qlo) && (q < qhi);
+        const long long rem = end_rel - 4ll * q;
+        const int nbytes = ok ? (rem >= 4 ? 16 : (int)rem * 4) : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src0 + 4 * q : x_al), "r"(nbytes) : "memory");
+        dst += ST_PER_CH * 16;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int g = 0; g < RAW_STAGES - 1; ++g) issue(g);
+  int as = 0, aph = 0;
+  int c_tile = -1, c_g0 = 0, c_b = 0, last_b = -1;
+  long long c_boff = 0;
+  // conversion mapping: warp parity -> K chunk, (warp / 2, lane) -> ROWS_PER_PASS rows per pass: every shared-memory access of
+  // a warp touches consecutive words / consecutive 16-byte rows
+  const int sw = warp - 2;
+  const int dbg_st = g_dbg;
+  const int kc = sw & 1, rg = (sw >> 1) * 32 + lane;
+  constexpr int NRC = (RW_MAX + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
+  const float xs_ = X_SCALE;
+  for (int g = 0; g < total_blocks; ++g) {
+    const int tl = g / ncb, cb = g - tl * ncb;
+    if (tl != c_tile) {
+      c_tile = tl;
+      const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
+      c_b = tc_.b;
+      c_boff = (long long)tc_.b * a.x_bstride;
+      c_g0 = tc_.tq * TN - a.pad;
+    }
+    asm volatile("cp.async.wait_group %0;" ::"n"(RAW_STAGES - 2) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));  // block g landed for everybody; block g-1 fully converted
+    issue(g + RAW_STAGES - 1);                             // reuses the slot of block g-1
+    if (c_b != last_b) {
+      // per-channel prologue coefficients of this utterance, with the 2^6 operand scale folded in: z' = 64 z = (64a) x + 64b;
+      // snake(z) * 64 = z' + (64/alpha) sin^2((alpha/64) z'); LeakyReLU is positively homogeneous
+      for (int c = st; c < cin_pad; c += NUM_STAGERS) {
+        float pa = 0.f, pb = 0.f, al = 1.f;  // padded channels stage exact zeros
+        if (c < Cin_) {
+          pa = 1.f;
+          if (has_affine) { pa = a.pre_a[c_b * Cin_ + c]; pb = a.pre_b[c_b * Cin_ + c]; }
+          if (is_snake) al = a.pre_alpha[c];
+        }
+        coef[c] = pa * xs_; coef[CIN_PAD_MAX + c] = pb * xs_; coef[2 * CIN_PAD_MAX + c] = al * (1.0f / X_SCALE);
+        coef[3 * CIN_PAD_MAX + c] = xs_ / al;
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(NUM_STAGERS));
+      last_b = c_b;
+    }
+    const int c0 = cb * CB + kc * 8;
+    float pa[8], pb[8], al[8], ia[8];
+    int sh[8];
+    {
+      const int sh0 = (int)((xaddr4 + (unsigned long long)(c_boff + (long long)c0 * Lin_ + c_g0)) & 3ull), lin3 = Lin_ & 3;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        pa[j] = coef[c0 + j]; pb[j] = coef[CIN_PAD_MAX + c0 + j]; al[j] = coef[2 * CIN_PAD_MAX + c0 + j];
+        ia[j] = coef[3 * CIN_PAD_MAX + c0 + j];
+        sh[j] = ((sh0 + j * lin3) & 3) + j * RAW_PITCH;   // 4-byte phase of channel c0+j's row start (padded channels: any)
+      }
+    }
+    const float* raw = reinterpret_cast<const float*>(smem + SM_RAW + (g % RAW_STAGES) * RAW_BYTES) + (kc * 8) * RAW_PITCH;
+    mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
+    uint8_t* p0 = smem + SM_ACT + as * ACT_BUF_BYTES;
+    uint8_t* p1 = p0 + ACT_PLANE_BYTES;
+#pragma unroll
+    for (int i = 0; i < NRC; ++i) {
+      const int r = rg + ROWS_PER_PASS * i;
+      if (r < RW && !(dbg_st & 4)) {
+        const int gt = c_g0 + r;
+        const bool inb = (gt >= 0) && (gt < Lin_);
+        float xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] = raw[sh[j] + r];
+        if (pre_act_ == ST2_ACT_SNAKE) stage_row<ST2_ACT_SNAKE, MODE>(xv, pa, pb, al, ia, slope_, inb, p0, p1, kc, r, RWP);
+        else if (pre_act_ == ST2_ACT_LRELU) stage_row<ST2_ACT_LRELU, MODE>(xv, pa, pb, al, ia, slope_, inb, p0, p1, kc, r, RWP);
+        else stage_row<ST2_ACT_NONE, MODE>(xv, pa, pb, al, ia, slope_, inb, p0, p1, kc, r, RWP);
+      }
+    }
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    mbar_arrive(BAR(B_AFULL + as));
+    if (++as == 2) { as = 0; aph ^= 1; }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int ncb, const int RW, const int ntiles,
@@ -434,158 +601,9 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     }
   } else if (warp == 1) {
     // ================================================================ weight producer (1-D TMA bulk copies)
-    // one copy per stage = up to TPS consecutive taps of one 16-channel block (contiguous in the [cob][cb][tap] layout)
-    if (lane == 0) {
-      const int dbg_p = g_dbg;
-      int ws = 0, wph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const TileCoord tc_ = tile_coord(tile, n_tq, n_cob);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(wtc) + (size_t)tc_.cob * ncb * K * W_STEP_BYTES;
-        for (int cb = 0; cb < ncb; ++cb) {
-          for (int tap0 = 0; tap0 < K; tap0 += TPS) {
-            const uint32_t bytes = (uint32_t)min(TPS, K - tap0) * W_STEP_BYTES;
-            mbar_wait(BAR(B_WEMPTY + ws), wph ^ 1);
-            if (dbg_p & 16) {
-              mbar_arrive(BAR(B_WFULL + ws));                    // timing experiment: no weight traffic
-            } else {
-              mbar_expect_tx(BAR(B_WFULL + ws), bytes);
-              bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, bytes, BAR(B_WFULL + ws));
-            }
-            src += bytes;
-            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
-          }
-        }
-      }
-    }
+    if (lane == 0) weight_producer_role(wtc, sbase, bar0, ncb, K, W_STEP_BYTES, TPS, ntiles, n_tq, n_cob);
   } else if (warp < 2 + NUM_STAGERS / 32) {
-    // ================================================================ activation stagers
-    // Raw fp32 frame windows travel HBM -> shared memory with 16-byte cp.async copies (no registers held while in
-    // flight): a ring of RAW_STAGES 16-channel blocks keeps ~60 KB per SM outstanding, which is what it takes to cover
-    // HBM latency.  Rows of the activation tensor start at any 4-byte phase (odd row lengths), so each channel row
-    // copies the 16-byte ALIGNED superset of its window; the phase (0..3 floats) is re-derived by the conversion.
-    // Chunks outside the tensor are zero-filled (src-size 0), the chunk that crosses the end of the tensor is
-    // trimmed; nothing before the 16-byte aligned start of the tensor's allocation is ever touched.
-    const int st = tid - 64;  // 0..319
-    const int Lin_ = a.Lin, pre_act_ = a.pre_act, Cin_ = a.Cin;
-    const float slope_ = a.pre_slope;
-    const bool has_affine = a.pre_a != nullptr, is_snake = pre_act_ == ST2_ACT_SNAKE;
-    float* coef = reinterpret_cast<float*>(smem + SM_COEF);
-    const int cin_pad = ncb * CB;
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total_blocks = my_tiles * ncb;
-    const unsigned long long xaddr4 = (unsigned long long)(uintptr_t)a.x >> 2;
-    const long long tensor_end = (long long)(a.B - 1) * a.x_bstride + (long long)Cin_ * Lin_;  // floats from a.x
-    const float* x_al = reinterpret_cast<const float*>((uintptr_t)a.x & ~(uintptr_t)15);
-    // issue mapping: thread -> one channel of the block and every ST_PER_CH-th 16-byte chunk of its row
-    const int ich = st / ST_PER_CH, iq0 = st - ich * ST_PER_CH;
-    int i_tile = -1, i_g0 = 0;  // producer-side tile state (runs RAW_STAGES-1 blocks ahead of the conversion)
-    long long i_boff = 0;
-    const int dbg_i = g_dbg;
-    auto issue = [&](int g) {
-      if (g < total_blocks && !(dbg_i & 32)) {
-        const int tl = g / ncb, cb = g - tl * ncb;
-        if (tl != i_tile) {
-          i_tile = tl;
-          const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
-          i_boff = (long long)tc_.b * a.x_bstride;
-          i_g0 = tc_.tq * TN - a.pad;
-        }
-        const int c = cb * CB + ich;
-        const long long e0 = i_boff + (long long)min(c, Cin_ - 1) * Lin_ + i_g0;   // first window element, floats from a.x
-        const int shift = (int)((xaddr4 + (unsigned long long)e0) & 3ull);
-        const int rlo = max(0, -i_g0), rhi = min(RW, Lin_ - i_g0);              // rows [rlo, rhi) are inside the tensor
-        int qlo = 0, qhi = 0;
-        if (c < Cin_ && rhi > rlo) { qlo = (rlo + shift) >> 2; qhi = (rhi + shift + 3) >> 2; }
-        const long long w0 = e0 - shift;                                          // aligned window start, floats from a.x
-        const float* src0 = a.x + w0;
-        const long long end_rel = tensor_end - w0;
-        uint32_t dst = sbase + SM_RAW + (g % RAW_STAGES) * RAW_BYTES + (uint32_t)(ich * RAW_PITCH + iq0 * 4) * 4;
-#pragma unroll
-        for (int i = 0; i < RAW_CHUNKS / ST_PER_CH; ++i) {
-          const int q = iq0 + ST_PER_CH * i;
-          const bool ok = (q >= qlo) && (q < qhi);
-          const long long rem = end_rel - 4ll * q;
-          const int nbytes = ok ? (rem >= 4 ? 16 : (int)rem * 4) : 0;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src0 + 4 * q : x_al), "r"(nbytes) : "memory");
-          dst += ST_PER_CH * 16;
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    for (int g = 0; g < RAW_STAGES - 1; ++g) issue(g);
-    int as = 0, aph = 0;
-    int c_tile = -1, c_g0 = 0, c_b = 0, last_b = -1;
-    long long c_boff = 0;
-    // conversion mapping: warp parity -> K chunk, (warp / 2, lane) -> ROWS_PER_PASS rows per pass: every shared-memory access of
-    // a warp touches consecutive words / consecutive 16-byte rows
-    const int sw = warp - 2;
-    const int dbg_st = g_dbg;
-    const int kc = sw & 1, rg = (sw >> 1) * 32 + lane;
-    constexpr int NRC = (RW_MAX + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
-    const float xs_ = X_SCALE;
-    for (int g = 0; g < total_blocks; ++g) {
-      const int tl = g / ncb, cb = g - tl * ncb;
-      if (tl != c_tile) {
-        c_tile = tl;
-        const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
-        c_b = tc_.b;
-        c_boff = (long long)tc_.b * a.x_bstride;
-        c_g0 = tc_.tq * TN - a.pad;
-      }
-      asm volatile("cp.async.wait_group %0;" ::"n"(RAW_STAGES - 2) : "memory");
-      asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));  // block g landed for everybody; block g-1 fully converted
-      issue(g + RAW_STAGES - 1);                             // reuses the slot of block g-1
-      if (c_b != last_b) {
-        // per-channel prologue coefficients of this utterance, with the 2^6 operand scale folded in: z' = 64 z = (64a) x + 64b;
-        // snake(z) * 64 = z' + (64/alpha) sin^2((alpha/64) z'); LeakyReLU is positively homogeneous
-        for (int c = st; c < cin_pad; c += NUM_STAGERS) {
-          float pa = 0.f, pb = 0.f, al = 1.f;  // padded channels stage exact zeros
-          if (c < Cin_) {
-            pa = 1.f;
-            if (has_affine) { pa = a.pre_a[c_b * Cin_ + c]; pb = a.pre_b[c_b * Cin_ + c]; }
-            if (is_snake) al = a.pre_alpha[c];
-          }
-          coef[c] = pa * xs_; coef[CIN_PAD_MAX + c] = pb * xs_; coef[2 * CIN_PAD_MAX + c] = al * (1.0f / X_SCALE);
-          coef[3 * CIN_PAD_MAX + c] = xs_ / al;
-        }
-        asm volatile("bar.sync 2, %0;" ::"n"(NUM_STAGERS));
-        last_b = c_b;
-      }
-      const int c0 = cb * CB + kc * 8;
-      float pa[8], pb[8], al[8], ia[8];
-      int sh[8];
-      {
-        const int sh0 = (int)((xaddr4 + (unsigned long long)(c_boff + (long long)c0 * Lin_ + c_g0)) & 3ull), lin3 = Lin_ & 3;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          pa[j] = coef[c0 + j]; pb[j] = coef[CIN_PAD_MAX + c0 + j]; al[j] = coef[2 * CIN_PAD_MAX + c0 + j];
-          ia[j] = coef[3 * CIN_PAD_MAX + c0 + j];
-          sh[j] = ((sh0 + j * lin3) & 3) + j * RAW_PITCH;   // 4-byte phase of channel c0+j's row start (padded channels: any)
-        }
-      }
-      const float* raw = reinterpret_cast<const float*>(smem + SM_RAW + (g % RAW_STAGES) * RAW_BYTES) + (kc * 8) * RAW_PITCH;
-      mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
-      uint8_t* p0 = smem + SM_ACT + as * ACT_BUF_BYTES;
-      uint8_t* p1 = p0 + ACT_PLANE_BYTES;
-#pragma unroll
-      for (int i = 0; i < NRC; ++i) {
-        const int r = rg + ROWS_PER_PASS * i;
-        if (r < RW && !(dbg_st & 4)) {
-          const int gt = c_g0 + r;
-          const bool inb = (gt >= 0) && (gt < Lin_);
-          float xv[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xv[j] = raw[sh[j] + r];
-          if (pre_act_ == ST2_ACT_SNAKE) stage_row<ST2_ACT_SNAKE, MODE>(xv, pa, pb, al, ia, slope_, inb, p0, p1, kc, r, RWP);
-          else if (pre_act_ == ST2_ACT_LRELU) stage_row<ST2_ACT_LRELU, MODE>(xv, pa, pb, al, ia, slope_, inb, p0, p1, kc, r, RWP);
-          else stage_row<ST2_ACT_NONE, MODE>(xv, pa, pb, al, ia, slope_, inb, p0, p1, kc, r, RWP);
-        }
-      }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(BAR(B_AFULL + as));
-      if (++as == 2) { as = 0; aph ^= 1; }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    stager_role<MODE>(a, smem, sbase, bar0, ncb, RW, ntiles, n_tq, n_cob, tid, warp, lane);
   } else {
     // ================================================================ epilogue (8 warps)
     const int ewi = warp - (2 + NUM_STAGERS / 32);  // 0..7
@@ -781,14 +799,316 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
   }
 }
 
-// One element of a weight stage block [plane 2][chunk 2][128 rows][16 B]: byte index -> value.
+// =============================================================================================
+// TIME-MAJOR variant for narrow layers (Cout <= 128; HiFi-GAN C = 64 / 32 stages, conv_post): the operand roles are
+// swapped --
+//     D[t (M = 128 per MMA, two M blocks per 256-frame tile), co (N = NC)] = sum_tap sum_ci z[ci, t + tap*dil - pad] * W_tap[co, ci]
+// The staged activation window is the A operand (same K-major 16-byte-row layout, a tap is still a descriptor shift, M block
+// 1 is the window advanced by 128 rows), the weights are the B operand with only NC = Cout rounded up to 32 (16 for
+// Cout <= 16) rows: no tensor-pipe time and no weight traffic is spent on absent output channels (the channel-major kernel
+// runs M = 128 for Cout = 32).  In TMEM a lane is a FRAME and a column is a channel, so an epilogue thread owns one frame
+// of every channel: a warp's store of one accumulator register is 128 contiguous bytes of one output row -- no transpose
+// through shared memory.  The InstanceNorm partials are reduced across the warp's 32 frames with a transposing shuffle tree
+// (62 shuffles per 32 channels for the sum and the sum of squares of the deviation from a pilot sample), the four warps of an
+// M block merge their (count, mean, M2) records through shared memory in fixed order: two partials per tile like the
+// channel-major kernel.  FAST recipe only.
+__host__ __device__ __forceinline__ int tmajor_nc(int Cout) { return Cout <= 16 ? 16 : ((Cout + 31) & ~31); }
+
+constexpr int SM_TSTAT = SM_EPI;                          // [2 tile parities][8 warps][128 channels][3] floats
+constexpr int SM_TBIAS = SM_TSTAT + 2 * 8 * 128 * 3 * 4;  // 128 floats
+constexpr int SM_TPILOT = SM_TBIAS + 512;                 // [8 warps][32] floats
+static_assert(SM_TPILOT + 8 * 32 * 4 <= SM_BAR, "time-major epilogue scratch");
+
+template <bool RES, int ACC>
+__device__ __forceinline__ void tct_rows(float (&v)[16], const float (&rv)[16], const float* bsm_c0, float* yp0, const unsigned ys,
+                                         const int nch, const bool tv, const float out_div, const float acc_div, const int out_act) {
+#pragma unroll
+  for (int j0 = 0; j0 < 16; j0 += 8) {
+    if (j0 < nch) {   // warp-uniform
+      float yo[8];
+      if (ACC) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) yo[i] = (tv && (j0 + i) < nch) ? yp0[(unsigned)(j0 + i) * ys] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int j = j0 + i;
+        float val = v[j] * D_UNSCALE + bsm_c0[j];
+        if (RES) val += rv[j];
+        if (out_div != 1.0f) val = __fdiv_rn(val, out_div);
+        if (ACC == 1) val = yo[i] + val;
+        if (ACC == 2) val = __fdiv_rn(yo[i] + val, acc_div);
+        if (out_act == ST2_ACT_TANH) val = tanhf(val);
+        const bool ok = tv && j < nch;
+        if (ok) yp0[(unsigned)j * ys] = val;
+        v[j] = ok ? val : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[j0 + i] = 0.f;
+    }
+  }
+}
+
+// One step of the transposing reduction: 2N values per lane -> N values per lane, each summed with the partner lane (lane ^ N).
+template <int N>
+__device__ __forceinline__ void xreduce_step(float* d, const int lane) {
+  const bool up = (lane & N) != 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float send = up ? d[i] : d[i + N];
+    const float keep = up ? d[i + N] : d[i];
+    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, N);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int ncb, const int RW, const int ntiles, const int n_tq,
+                  const int NC) {
+  constexpr int MODE = MODE_FAST;
+  const int RWP = RW + 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + SM_BAR;
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * B_COUNT);
+
+  if (tid == 0) {
+    for (int i = 0; i < W_STAGES; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(B_AFULL + i), NUM_STAGERS);
+      mbar_init(BAR(B_AEMPTY + i), 1);
+      mbar_init(BAR(B_TFULL + i), 1);
+      mbar_init(BAR(B_TEMPTY + i), NUM_EPI);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int K = a.K;
+  const int wstep = 64 * NC;                      // bytes of one (16 channels, tap) step: 2 planes x 2 chunks x NC rows x 16 B
+  const int tps = W_STAGE_BYTES / wstep;          // taps per weight stage: 2 (NC = 128) .. 16 (NC = 16)
+
+  if (warp == 0) {
+    // ================================================================ MMA issuer (converged warp, one elected lane)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);   // D = f32, M = 128, N = NC
+    const uint32_t elected = elect_one();
+    const uint64_t dx_d = make_desc(sbase + SM_ACT, (uint32_t)RWP * 16, 128), dw_d = make_desc(sbase + SM_W, (uint32_t)NC * 16, 128);
+    const uint32_t dx_lo0 = (uint32_t)dx_d, dx_hi = (uint32_t)(dx_d >> 32), dw_lo0 = (uint32_t)dw_d, dw_hi = (uint32_t)(dw_d >> 32);
+    const uint32_t dil_ = (uint32_t)a.dil, wplane16 = (uint32_t)(2 * NC), wstep16 = (uint32_t)(4 * NC);
+    int ws = 0, wph = 0, as = 0, aph = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(BAR(B_TEMPTY + buf), ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(buf * 2 * NC);   // M block 0; M block 1 at + NC columns
+      uint32_t acc = 0;
+      for (int cb = 0; cb < ncb; ++cb) {
+        mbar_wait(BAR(B_AFULL + as), aph);
+        tc_fence_after();
+        uint32_t x_lo = dx_lo0 + (uint32_t)as * (ACT_BUF_BYTES >> 4);
+        for (int tap0 = 0; tap0 < K; tap0 += tps) {
+          mbar_wait(BAR(B_WFULL + ws), wph);
+          tc_fence_after();
+          const int nt = min(tps, K - tap0);
+          if (elected) {
+            uint32_t w_lo = dw_lo0 + (uint32_t)ws * (W_STAGE_BYTES >> 4);
+            for (int t = 0; t < nt; ++t) {
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                tc_mma_w(d0 + (uint32_t)(m * NC), x_lo + 128u * m, dx_hi, w_lo, dw_hi, idesc, acc);
+                tc_mma_f8_w(d0 + (uint32_t)(m * NC), x_lo + 128u * m + (ACT_PLANE_BYTES >> 4), dx_hi, w_lo + wplane16, dw_hi, idesc, 1u);
+              }
+              acc = 1;
+              w_lo += wstep16;
+              x_lo += dil_;
+            }
+            tc_commit(BAR(B_WEMPTY + ws));
+          } else {
+            acc = 1;
+            x_lo += dil_ * (uint32_t)nt;
+          }
+          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+        }
+        if (elected) tc_commit(BAR(B_AEMPTY + as));
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+      if (elected) tc_commit(BAR(B_TFULL + buf));
+    }
+  } else if (warp == 1) {
+    // ================================================================ weight producer (1-D TMA bulk copies)
+    if (lane == 0) weight_producer_role(wtc, sbase, bar0, ncb, K, wstep, tps, ntiles, n_tq, 1);
+  } else if (warp < 2 + NUM_STAGERS / 32) {
+    stager_role<MODE>(a, smem, sbase, bar0, ncb, RW, ntiles, n_tq, 1, tid, warp, lane);
+  } else {
+    // ================================================================ epilogue (8 warps): warp -> (M block, 32 frames)
+    // The work of a warp is the sequence of (tile, 16-channel group) steps of its frames.  The residual values of step s+1
+    // are loaded (16 registers, one 128-byte row piece per warp instruction) before step s is processed -- across tile
+    // boundaries too -- so their latency hides behind one step of TMEM load, stores and statistics.
+    const int ewi = warp - (2 + NUM_STAGERS / 32);  // 0..7
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access = frames 32q .. 32q+31 of the M block
+    const int m = ewi >> 2;                          // M block (which 128 frames of the tile)
+    const int et = tid - (64 + NUM_STAGERS);         // 0..255
+    float* sstat = reinterpret_cast<float*>(smem + SM_TSTAT);
+    float* bsm = reinterpret_cast<float*>(smem + SM_TBIAS);
+    float* pil = reinterpret_cast<float*>(smem + SM_TPILOT) + ewi * 32;
+    const int y_len_ = a.y_len, res_len_ = a.res_len, acc_ = a.accum_mode, out_act_ = a.out_act, Cout_ = a.Cout, Lq_ = a.Lq;
+    const int ytst_ = a.y_tstride, ytoff_ = a.y_toffset, rshift_ = a.res_shift;
+    const float out_div_ = a.out_div, acc_div_ = a.accum_div;
+    const bool has_stats = a.stats != nullptr, has_res = a.res != nullptr;
+    const int ng = NC >> 4;                          // 16-channel groups per tile
+    const int fr0 = m * 128 + q * 32;                // first frame of this warp within a tile
+    if (et < 128) bsm[et] = (a.bias && et < Cout_) ? a.bias[et] : 0.f;
+    asm volatile("bar.sync 5, %0;" ::"n"(NUM_EPI));
+    float rvn[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rvn[j] = 0.f;
+    // residual values of group gi of tile `tile_` -> rvn (zeros where the frame or the channel does not exist)
+    auto prefetch = [&](int tile_, int gi) {
+      if (has_res && tile_ < ntiles) {
+        const int tq_ = tile_ % n_tq, b_ = tile_ / n_tq;
+        const int tl_ = fr0 + lane;
+        const bool tv_ = tl_ < min(TN, Lq_ - tq_ * TN);
+        const int oidx_ = (tq_ * TN + tl_) * ytst_ + ytoff_;
+        const float* r0 = a.res + (long long)b_ * a.res_bstride + (long long)(gi * 16) * res_len_ + (oidx_ >> rshift_);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rvn[j] = (tv_ && (gi * 16 + j) < Cout_) ? __ldg(r0 + (unsigned)j * (unsigned)res_len_) : 0.f;
+      }
+    };
+    prefetch(blockIdx.x, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int tq = tile % n_tq, b = tile / n_tq;
+      const int buf = it & 1;
+      const int t0 = tq * TN;
+      const int ncols = min(TN, Lq_ - t0);
+      const int tl = fr0 + lane;                       // frame within the tile
+      const bool tv = tl < ncols;
+      const int nvalid = max(0, min(32, ncols - fr0));   // warp-uniform
+      const int oidx = (t0 + tl) * ytst_ + ytoff_;
+      float* yp = a.y + (long long)b * a.y_bstride + oidx;
+      float* sst = sstat + ((it & 1) * 8 + ewi) * 128 * 3;
+      for (int gi = 0; gi < ng; ++gi) {
+        const int c0 = gi * 16;
+        float rv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rv[j] = rvn[j];
+        if (gi + 1 < ng) prefetch(tile, gi + 1);
+        else prefetch(tile + gridDim.x, 0);
+        if (gi == 0) {
+          mbar_wait(BAR(B_TFULL + buf), (it >> 1) & 1);
+          tc_fence_after();
+        }
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * NC + m * NC + c0), v);
+        if (gi + 1 == ng) {   // last group: the accumulator is free for the MMAs of the tile after next
+          tc_fence_before();
+          mbar_arrive(BAR(B_TEMPTY + buf));
+        }
+        const int nch = min(16, Cout_ - c0);   // warp-uniform, may be <= 0 for padded channel groups
+        if (nch <= 0 || nvalid == 0) continue;
+        float* yp0 = yp + (long long)c0 * y_len_;
+        const float* bs0 = bsm + c0;
+        const unsigned ys = (unsigned)y_len_;
+        if (has_res) {
+          if (acc_ == 0) tct_rows<true, 0>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+          else if (acc_ == 1) tct_rows<true, 1>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+          else tct_rows<true, 2>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+        } else {
+          if (acc_ == 0) tct_rows<false, 0>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+          else if (acc_ == 1) tct_rows<false, 1>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+          else tct_rows<false, 2>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+        }
+        if (has_stats) {
+          // pilot sample per channel = the value of the warp's first frame (always valid when nvalid > 0)
+          if (lane == 0) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              *reinterpret_cast<float4*>(&pil[4 * k4]) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 p4 = *reinterpret_cast<const float4*>(&pil[4 * k4]);
+            v[4 * k4] = tv ? v[4 * k4] - p4.x : 0.f;
+            v[4 * k4 + 1] = tv ? v[4 * k4 + 1] - p4.y : 0.f;
+            v[4 * k4 + 2] = tv ? v[4 * k4 + 2] - p4.z : 0.f;
+            v[4 * k4 + 3] = tv ? v[4 * k4 + 3] - p4.w : 0.f;
+          }
+          {  // lanes L and L^16 hold the same 16 channels: the lower lane continues with the sums, the upper one with the squares
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float o = __shfl_xor_sync(0xffffffffu, v[i], 16);
+              v[i] = up ? fmaf(v[i], v[i], o * o) : v[i] + o;
+            }
+          }
+          xreduce_step<8>(v, lane);
+          xreduce_step<4>(v, lane);
+          xreduce_step<2>(v, lane);
+          xreduce_step<1>(v, lane);
+          // lane L < 16: S1 (sum of deviations from the pilot) of channel c0 + L; lane 16 + L: S2 (sum of their squares)
+          const float s2 = __shfl_down_sync(0xffffffffu, v[0], 16);
+          const float nn = (float)nvalid;
+          const float pl = pil[lane & 15];
+          if (lane < nch) {
+            float* sp = sst + (c0 + lane) * 3;
+            sp[0] = nn; sp[1] = pl + v[0] / nn; sp[2] = fmaxf(0.f, s2 - v[0] * v[0] / nn);
+          }
+          __syncwarp();
+        }
+      }
+      if (has_stats) {
+        if (nvalid == 0) {   // this warp's frames are beyond the row: empty records for every channel
+          for (int c = lane; c < Cout_; c += 32) { sst[c * 3] = 0.f; sst[c * 3 + 1] = 0.f; sst[c * 3 + 2] = 0.f; }
+        }
+        // the four warps of an M block merge their records in fixed order: one partial per (tile, M block, channel)
+        asm volatile("bar.sync %0, 128;" ::"r"(3 + m) : "memory");
+        const int co = et & 127;
+        if (co < Cout_) {
+          float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const float* sp = sstat + (((it & 1) * 8 + m * 4 + qq) * 128 + co) * 3;
+            const float nb = sp[0], mb = sp[1], qb = sp[2];
+            if (nb > 0.f) {
+              const float nn = n + nb, dl = mb - mean;
+              mean += dl * (nb / nn);
+              m2 += qb + dl * dl * (n * nb / nn);
+              n = nn;
+            }
+          }
+          float* gp = a.stats + (((long long)b * Cout_ + co) * a.stats_nparts + a.stats_part_offset + 2 * tq + m) * 3;
+          gp[0] = n; gp[1] = mean; gp[2] = m2;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// One element of a weight stage block [plane 2][chunk 2][rows][16 B] (rows = 128, or NC for the time-major layout): byte index -> value.
 //   plane 0: fp16 high plane of w' = w * 2^12, chunk = channels 8*kc .. 8*kc+7 (2 bytes each).
 //   plane 1, ST2_TC_FAST: e4m3 bytes; chunk 0 = l(w') * 2^4 for the block's 16 channels, chunk 1 = h(w') * 2^-8.
 //   plane 1, otherwise:   fp16 low plane l(w') (* 2^8 for ST2_TC_ACCURATE).
-__device__ __forceinline__ void weight_stage_store(uint8_t* blk, int byte_in_stage, int mode, const float* wrow16 /* 16 channel values of this row */) {
-  const int plane = byte_in_stage / W_PLANE_BYTES;
-  const int r = byte_in_stage % W_PLANE_BYTES;
-  const int chunk = r / (TM * 16), within = r % 16;
+__device__ __forceinline__ void weight_stage_store(uint8_t* blk, int byte_in_stage, int mode, const float* wrow16 /* 16 channel values of this row */,
+                                                   int rows) {
+  const int plane_bytes = KCB * rows * 16;
+  const int plane = byte_in_stage / plane_bytes;
+  const int r = byte_in_stage % plane_bytes;
+  const int chunk = r / (rows * 16), within = r % 16;
   if (plane == 0 || mode != MODE_FAST) {
     if (within & 1) return;       // handled by the even byte
     const float wv = wrow16[chunk * 8 + within / 2] * W_SCALE;
@@ -804,63 +1124,71 @@ __device__ __forceinline__ void weight_stage_store(uint8_t* blk, int byte_in_sta
   }
 }
 
-// fp32 [Cout,Cin,K] -> step blocks [n_cob][ncb][K] x 8 KB (the taps of one 16-channel block are contiguous)
+// Row `col` of output-channel block `cob` -> output channel (or -1): channel-major layout spreads the channels over the four
+// TMEM lane quarters (rows_per_quarter), the time-major layout (rows = NC, one block) is the identity.
+__device__ __forceinline__ int weight_row_channel(int Cout, int cob, int col, bool tmajor) {
+  if (tmajor) return col < Cout ? col : -1;
+  const int rq = rows_per_quarter(Cout, cob);
+  const int qq = col >> 5, rr = col & 31;
+  const int co = cob * TM + qq * rq + rr;
+  return (rr < rq && co < Cout) ? co : -1;
+}
+
+// fp32 [Cout,Cin,K] -> step blocks [n_cob][ncb][K] x (64 * rows) bytes (the taps of one 16-channel block are contiguous)
 __global__ void conv_tc_weight_layout_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int Cout, int Cin, int K,
-                                             int n_cob, int ncb, int mode) {
+                                             int n_cob, int ncb, int mode, int rows, int tmajor) {
   // one thread per (stage, plane, chunk, row): writes the 16 bytes of that row
-  const long long total = (long long)K * n_cob * ncb * 2 * KCB * TM;
+  const long long total = (long long)K * n_cob * ncb * 2 * KCB * rows;
+  const int step_bytes = 2 * KCB * rows * 16;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
-    const int col = (int)(r % TM); r /= TM;
+    const int col = (int)(r % rows); r /= rows;
     const int chunk = (int)(r % KCB); r /= KCB;
     const int plane = (int)(r % 2); r /= 2;
     const int cb = (int)(r % ncb); r /= ncb;
     const int cob = (int)(r % n_cob); r /= n_cob;
     const int tap = (int)r;
-    const int rq = rows_per_quarter(Cout, cob);
-    const int qq = col >> 5, rr = col & 31;
-    const int co = cob * TM + qq * rq + rr;
+    const int co = weight_row_channel(Cout, cob, col, tmajor != 0);
     float wr[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int ci = cb * CB + j;
-      wr[j] = (rr < rq && co < Cout && ci < Cin) ? w[((long long)co * Cin + ci) * K + tap] : 0.f;
+      wr[j] = (co >= 0 && ci < Cin) ? w[((long long)co * Cin + ci) * K + tap] : 0.f;
     }
-    uint8_t* blk = out + (((long long)cob * ncb + cb) * K + tap) * W_STEP_BYTES;
-    const int base = plane * W_PLANE_BYTES + (chunk * TM + col) * 16;
+    uint8_t* blk = out + (((long long)cob * ncb + cb) * K + tap) * step_bytes;
+    const int base = plane * (KCB * rows * 16) + (chunk * rows + col) * 16;
 #pragma unroll
-    for (int b = 0; b < 16; ++b) weight_stage_store(blk, base + b, mode, wr);
+    for (int b = 0; b < 16; ++b) weight_stage_store(blk, base + b, mode, wr, rows);
   }
 }
 
 // ConvTranspose1d weight [Cin,Cout,K] -> S per-phase tensor-core blocks (phase r = J-tap stride-1 conv, see conv.cu)
 __global__ void convT_tc_weight_layout_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int Cin, int Cout, int K,
-                                              int S, int P, int J, int n_cob, int ncb, int mode) {
-  const long long per_phase = (long long)J * n_cob * ncb * 2 * KCB * TM;
+                                              int S, int P, int J, int n_cob, int ncb, int mode, int rows, int tmajor) {
+  const long long per_phase = (long long)J * n_cob * ncb * 2 * KCB * rows;
   const long long total = per_phase * S;
+  const int step_bytes = 2 * KCB * rows * 16;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ph = (int)(i / per_phase);
     long long r = i % per_phase;
-    const int col = (int)(r % TM); r /= TM;
+    const int col = (int)(r % rows); r /= rows;
     const int chunk = (int)(r % KCB); r /= KCB;
     const int plane = (int)(r % 2); r /= 2;
     const int cb = (int)(r % ncb); r /= ncb;
     const int cob = (int)(r % n_cob); r /= n_cob;
     const int kp = (int)r;  // tap of the phase conv
-    const int rq = rows_per_quarter(Cout, cob);
-    const int qq = col >> 5, rr = col & 31;
-    const int co = cob * TM + qq * rq + rr;
+    const int co = weight_row_channel(Cout, cob, col, tmajor != 0);
     const int kk = (J - 1 - kp) * S + ((ph + P) % S);
     float wr[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int ci = cb * CB + j;
-      wr[j] = (rr < rq && co < Cout && ci < Cin && kk < K) ? w[((long long)ci * Cout + co) * K + kk] : 0.f;
+      wr[j] = (co >= 0 && ci < Cin && kk < K) ? w[((long long)ci * Cout + co) * K + kk] : 0.f;
     }
-    uint8_t* blk = out + ((long long)ph * J * n_cob * ncb + ((long long)cob * ncb + cb) * J + kp) * W_STEP_BYTES;
-    const int base = plane * W_PLANE_BYTES + (chunk * TM + col) * 16;
+    uint8_t* blk = out + ((long long)ph * J * n_cob * ncb + ((long long)cob * ncb + cb) * J + kp) * step_bytes;
+    const int base = plane * (KCB * rows * 16) + (chunk * rows + col) * 16;
 #pragma unroll
-    for (int b = 0; b < 16; ++b) weight_stage_store(blk, base + b, mode, wr);
+    for (int b = 0; b < 16; ++b) weight_stage_store(blk, base + b, mode, wr, rows);
   }
 }
 
@@ -925,8 +1253,18 @@ __global__ void __launch_bounds__(256) convT_interleave_kernel(const float* __re
   }
 }
 
+constexpr int TMAJOR = ST2_TC_TMAJOR;   // flag bit of `mode`: time-major weight layout + kernel
+
+// bytes of the weight blocks of one stride-1 convolution in the layout `mode` asks for
+static long long weight_bytes_mode(int Cout, int Cin, int K, int mode) {
+  const int ncb = cdiv(Cin, CB);
+  if (mode & TMAJOR) return (long long)K * ncb * 64 * tmajor_nc(Cout);
+  return (long long)K * cdiv(Cout, TM) * ncb * W_STEP_BYTES;
+}
+
 static int launch_tc(const st2_conv_args& a, const void* wtc, int mode, int max_ctas, cudaStream_t st) {
-  const int n_tq = cdiv(a.Lq, TN), n_cob = cdiv(a.Cout, TM), ncb = cdiv(a.Cin, CB);
+  const bool tmajor = (mode & TMAJOR) != 0;
+  const int n_tq = cdiv(a.Lq, TN), n_cob = tmajor ? 1 : cdiv(a.Cout, TM), ncb = cdiv(a.Cin, CB);
   const int rw = (TN + (a.K - 1) * a.dil + 7) & ~7;
   const int ntiles = a.B * n_cob * n_tq;
   static int num_sms[64] = {0};   // per device ordinal (cudaFuncSetAttribute is per device too)
@@ -938,10 +1276,12 @@ static int launch_tc(const st2_conv_args& a, const void* wtc, int mode, int max_
     cudaFuncSetAttribute(conv1d_tc_kernel<MODE_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     cudaFuncSetAttribute(conv1d_tc_kernel<MODE_ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     cudaFuncSetAttribute(conv1d_tc_kernel<MODE_X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    cudaFuncSetAttribute(conv1d_tct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
   }
   int grid = ntiles < num_sms[dev] ? ntiles : num_sms[dev];
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  if (mode == MODE_FAST) conv1d_tc_kernel<MODE_FAST><<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
+  if (tmajor) conv1d_tct_kernel<<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, tmajor_nc(a.Cout));
+  else if (mode == MODE_FAST) conv1d_tc_kernel<MODE_FAST><<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
   else if (mode == MODE_ACC) conv1d_tc_kernel<MODE_ACC><<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
   else conv1d_tc_kernel<MODE_X3><<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
   ++g_launches;
@@ -957,15 +1297,23 @@ extern "C" {
 
 long long st2_conv_tc_weight_bytes(int Cout, int Cin, int K) {
   const int n_cob = cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB);
-  return (long long)K * n_cob * ncb * tc::W_STEP_BYTES;
+  return (long long)K * n_cob * ncb * tc::W_STEP_BYTES;   // upper bound for every layout (the time-major one is smaller)
 }
 
-static bool tc_mode_ok(int mode) { return mode == ST2_TC_FAST || mode == ST2_TC_ACCURATE || mode == ST2_TC_F16X3; }
+// recipes 0..2; the time-major flag only with the FAST recipe and Cout <= 128 (one accumulator pair per tile)
+static bool tc_mode_ok(int mode, int Cout) {
+  const int base = mode & ~tc::TMAJOR;
+  if (!(base == ST2_TC_FAST || base == ST2_TC_ACCURATE || base == ST2_TC_F16X3)) return false;
+  if (mode & tc::TMAJOR) return base == ST2_TC_FAST && Cout <= 128;
+  return true;
+}
 
 int st2_conv_tc_weight_layout(const float* w, void* out, int Cout, int Cin, int K, int mode, void* stream) {
-  ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0 && tc_mode_ok(mode), "st2_conv_tc_weight_layout", "bad args");
-  const int n_cob = cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB);
-  tc::conv_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)out, Cout, Cin, K, n_cob, ncb, mode);
+  ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0 && tc_mode_ok(mode, Cout), "st2_conv_tc_weight_layout", "bad args");
+  const bool tm = (mode & tc::TMAJOR) != 0;
+  const int n_cob = tm ? 1 : cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB), rows = tm ? tc::tmajor_nc(Cout) : tc::TM;
+  tc::conv_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)out, Cout, Cin, K, n_cob, ncb, mode & ~tc::TMAJOR,
+                                                                             rows, tm ? 1 : 0);
   ++g_launches;
   ST2_CHECK_LAUNCH("st2_conv_tc_weight_layout");
   return 0;
@@ -977,9 +1325,10 @@ int st2_conv_tc_supported(int Cin, int Cout, int K, int stride, int dil) {
 }
 
 int st2_conv1d_tc(const st2_conv_args* a, const void* wtc, int mode, int max_ctas, void* stream) {
-  ST2_REQUIRE(a && a->x && wtc && a->y && tc_mode_ok(mode), "st2_conv1d_tc", "null pointer / bad mode");
+  ST2_REQUIRE(a && a->x && wtc && a->y && tc_mode_ok(mode, a->Cout), "st2_conv1d_tc", "null pointer / bad mode");
   ST2_REQUIRE(st2_conv_tc_supported(a->Cin, a->Cout, a->K, a->stride, a->dil), "st2_conv1d_tc", "unsupported shape");
   ST2_REQUIRE(a->pre_act != ST2_ACT_SNAKE || a->pre_alpha, "st2_conv1d_tc", "snake prologue needs alpha");
+  ST2_REQUIRE(!(mode & tc::TMAJOR) || a->dup_q0_to < 0, "st2_conv1d_tc", "time-major kernel: no reflection duplicate");
   const int n_tq = cdiv(a->Lq, tc::TN);
   ST2_REQUIRE(!a->stats || a->stats_nparts >= a->stats_part_offset + 2 * n_tq, "st2_conv1d_tc", "stats buffer too small (2 partials per 256-column tile)");
   tc::launch_tc(*a, wtc, mode, max_ctas, (cudaStream_t)stream);
@@ -1006,17 +1355,19 @@ long long st2_convT_tc_weight_bytes(int Cin, int Cout, int K, int S) {
 }
 
 int st2_convT_tc_weight_layout(const float* w, void* out, int Cin, int Cout, int K, int S, int P, int mode, void* stream) {
-  ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0 && S > 0 && tc_mode_ok(mode), "st2_convT_tc_weight_layout", "bad args");
+  ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0 && S > 0 && tc_mode_ok(mode, Cout), "st2_convT_tc_weight_layout", "bad args");
   const int J = (K + S - 1) / S;
-  const int n_cob = cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB);
-  tc::convT_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)out, Cin, Cout, K, S, P, J, n_cob, ncb, mode);
+  const bool tm = (mode & tc::TMAJOR) != 0;
+  const int n_cob = tm ? 1 : cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB), rows = tm ? tc::tmajor_nc(Cout) : tc::TM;
+  tc::convT_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)out, Cin, Cout, K, S, P, J, n_cob, ncb,
+                                                                              mode & ~tc::TMAJOR, rows, tm ? 1 : 0);
   ++g_launches;
   ST2_CHECK_LAUNCH("st2_convT_tc_weight_layout");
   return 0;
 }
 
 int st2_conv_transpose1d_tc(const st2_conv_args* a0, const void* wtc, int mode, int K, int S, int P, int reflect_left1, void* stream) {
-  ST2_REQUIRE(a0 && a0->x && wtc && a0->y && tc_mode_ok(mode), "st2_conv_transpose1d_tc", "null pointer / bad mode");
+  ST2_REQUIRE(a0 && a0->x && wtc && a0->y && tc_mode_ok(mode, a0->Cout) && !(mode & tc::TMAJOR), "st2_conv_transpose1d_tc", "null pointer / bad mode");
   ST2_REQUIRE(K > 0 && S > 0 && P >= 0, "st2_conv_transpose1d_tc", "bad shape");
   const int J = (K + S - 1) / S;
   ST2_REQUIRE(st2_conv_tc_supported(a0->Cin, a0->Cout, J, 1, 1), "st2_conv_transpose1d_tc", "unsupported shape");
@@ -1046,12 +1397,12 @@ int st2_conv_transpose1d_tc(const st2_conv_args* a0, const void* wtc, int mode, 
  * interleaves, adds the residual and produces ONE statistics record per row (stats [B,Cout,1,3]). */
 int st2_conv_transpose1d_tc2(const st2_conv_args* a0, const void* wtc, int mode, int K, int S, int P, int reflect_left1, float* tmp,
                              void* stream) {
-  ST2_REQUIRE(a0 && a0->x && wtc && a0->y && tmp && tc_mode_ok(mode), "st2_conv_transpose1d_tc2", "null pointer / bad mode");
+  ST2_REQUIRE(a0 && a0->x && wtc && a0->y && tmp && tc_mode_ok(mode, a0->Cout), "st2_conv_transpose1d_tc2", "null pointer / bad mode");
   ST2_REQUIRE(K > 0 && S > 0 && P >= 0, "st2_conv_transpose1d_tc2", "bad shape");
   const int J = (K + S - 1) / S;
   ST2_REQUIRE(st2_conv_tc_supported(a0->Cin, a0->Cout, J, 1, 1), "st2_conv_transpose1d_tc2", "unsupported shape");
   ST2_REQUIRE(!a0->stats || a0->stats_nparts == 1, "st2_conv_transpose1d_tc2", "stats must have exactly one partial per row");
-  const long long phase_bytes = st2_conv_tc_weight_bytes(a0->Cout, a0->Cin, J);
+  const long long phase_bytes = tc::weight_bytes_mode(a0->Cout, a0->Cin, J, mode);
   const long long phase_stride = (long long)a0->B * a0->Cout * a0->Lin;
   for (int r = 0; r < S; ++r) {
     st2_conv_args a = *a0;

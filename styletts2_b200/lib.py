@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libstyletts2_b200.so")
 
 ACT_NONE, ACT_LRELU, ACT_SNAKE, ACT_TANH, ACT_GELU, ACT_GELU_TANH = 0, 1, 2, 3, 4, 5
 TC_FAST, TC_ACCURATE, TC_F16X3 = 0, 1, 2      # precision recipes of the tensor-core conv (include/styletts2_b200.h)
+TC_TMAJOR = 16                               # flag: time-major layout + kernel for narrow layers (FAST recipe, Cout <= 128)
 ABI_VERSION = 2
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import lib as L
-from .lib import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SNAKE, ACT_TANH, TC_ACCURATE, TC_FAST, TC_F16X3, ConvArgs, RowsArgs, ptr, stream_ptr
+from .lib import ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SNAKE, ACT_TANH, TC_ACCURATE, TC_FAST, TC_F16X3, TC_TMAJOR, ConvArgs, RowsArgs, ptr, stream_ptr
 
 f32 = torch.float32
 
@@ -144,15 +144,23 @@ class TCWeights:
 TC_MODE_OVERRIDE = os.environ.get("ST2_TC_MODE")   # A/B testing: force one recipe ("0" fast, "1" accurate, "2" f16x3)
 
 
-def _tc_mode(mode):
-    return int(TC_MODE_OVERRIDE) if TC_MODE_OVERRIDE is not None else int(mode)
+# Layers with at most this many output channels run the TIME-MAJOR kernel (frames on the MMA's M axis, Cout on N): HiFi-GAN's
+# C = 64 / 32 stages, conv_post.  0 disables; 128 is the kernel's limit.
+TC_TMAJOR_MAX_COUT = int(os.environ.get("ST2_TC_TMAJOR_MAX", "64"))
+
+
+def _tc_mode(mode, cout=None):
+    m = int(TC_MODE_OVERRIDE) if TC_MODE_OVERRIDE is not None else int(mode)
+    if cout is not None and m == TC_FAST and cout <= min(TC_TMAJOR_MAX_COUT, 128):
+        m |= TC_TMAJOR
+    return m
 
 
 def conv_tc_weight_layout(w: torch.Tensor, mode: int = TC_FAST) -> TCWeights:
     """folded fp32 [Cout,Cin,K] -> plane-split stage blocks for st2_conv1d_tc"""
     w = w.detach().contiguous()
     co, ci, k = w.shape
-    mode = _tc_mode(mode)
+    mode = _tc_mode(mode, co)
     nbytes = int(L.load().st2_conv_tc_weight_bytes(co, ci, k))
     out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     L.call("st2_conv_tc_weight_layout", ptr(w), ptr(out), co, ci, k, mode, stream_ptr())
@@ -183,7 +191,7 @@ def conv1d(x, wt, bias=None, *, K, stride=1, dil=1, pad=0, pre=None, pre_act=ACT
     nbytes = 4.0 * B * (Lin * Cin + Lout * Cout * ((2 if res is not None else 1) + (1 if accum_mode else 0)))
     flops = 2.0 * B * Cin * Cout * K * Lout
     if use_tc:
-        with _prof(f"conv1d_tc m{wtc.mode} ci{Cin} co{Cout} k{K} d{dil} L{Lout} B{B}", flops, nbytes, 2 if wtc.mode == TC_FAST else 3):
+        with _prof(f"conv1d_tc m{wtc.mode} ci{Cin} co{Cout} k{K} d{dil} L{Lout} B{B}", flops, nbytes, 2 if (wtc.mode & 15) == TC_FAST else 3):
             L.call("st2_conv1d_tc", C.byref(a), ptr(wtc.buf), wtc.mode, tc_max_ctas, stream_ptr())
     else:
         with _prof(f"conv1d_simt ci{Cin} co{Cout} k{K} s{stride} L{Lout} B{B}", flops, nbytes):
@@ -205,7 +213,7 @@ def convT_tc_weight_layout(w: torch.Tensor, stride: int, padding: int, mode: int
     """folded fp32 ConvTranspose1d weight [Cin,Cout,K] -> per-phase tensor-core blocks"""
     w = w.detach().contiguous()
     ci, co, k = w.shape
-    mode = _tc_mode(mode)
+    mode = _tc_mode(mode, co)
     nbytes = int(L.load().st2_convT_tc_weight_bytes(ci, co, k, stride))
     out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
     L.call("st2_convT_tc_weight_layout", ptr(w), ptr(out), ci, co, k, stride, padding, mode, stream_ptr())
@@ -225,6 +233,8 @@ def conv_transpose1d(x, wp, bias, *, K, stride, padding, pre_act=ACT_NONE, slope
         out = empty(B, Cout, Lout, device=x.device)
     use_tc = wtc is not None and USE_TC
     phase_major = use_tc and CONVT_PHASE_MAJOR and out.stride(2) == 1 and out.stride(1) == Lout
+    if use_tc and not phase_major and (wtc.mode & TC_TMAJOR):
+        use_tc = False   # the direct (strided-store) variant has no time-major kernel: FP32-pipe path
     nparts = 1 if phase_major else S * stats_parts(Lin) * (2 if use_tc else 1)
     stats = empty(B, Cout, nparts, 3, device=x.device) if want_stats else None
     a = ConvArgs()
@@ -235,7 +245,7 @@ def conv_transpose1d(x, wp, bias, *, K, stride, padding, pre_act=ACT_NONE, slope
     nbytes = 4.0 * B * (Lin * Cin + Lout * Cout * (2 if res is not None else 1))
     flops = 2.0 * B * Cin * Cout * J * S * Lin
     if use_tc:
-        with _prof(f"convT_tc m{wtc.mode} ci{Cin} co{Cout} k{K} s{S} L{Lin} B{B}", flops, nbytes, 2 if wtc.mode == TC_FAST else 3):
+        with _prof(f"convT_tc m{wtc.mode} ci{Cin} co{Cout} k{K} s{S} L{Lin} B{B}", flops, nbytes, 2 if (wtc.mode & 15) == TC_FAST else 3):
             if phase_major:
                 tmp = empty(S * B * Cout * Lin, device=x.device)
                 L.call("st2_conv_transpose1d_tc2", C.byref(a), ptr(wtc.buf), wtc.mode, K, S, padding, 1 if reflect_left1 else 0, ptr(tmp),
