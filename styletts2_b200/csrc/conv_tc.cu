@@ -284,8 +284,8 @@ __device__ __forceinline__ void epi_rows_vec(float* T, const float* bsm, float* 
 // Weight producer role (one lane of warp 1): one 1-D TMA bulk copy per pipeline stage = up to `tps` consecutive taps of one
 // 16-channel block (contiguous in the [cob][cb][tap] layout), `wstep` bytes per (16 channels, tap) step.
 __device__ __forceinline__ void weight_producer_role(const uint4* __restrict__ wtc, const uint32_t sbase, const uint32_t bar0,
-                                                     const int ncb, const int K, const int wstep, const int tps, const int ntiles,
-                                                     const int n_tq, const int n_cob) {
+                                                     const int ncb, const int K, const int wstep, const int tps, const int stage_bytes,
+                                                     const int ntiles, const int n_tq, const int n_cob) {
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   const int dbg_p = g_dbg;
   int ws = 0, wph = 0;
@@ -300,7 +300,7 @@ __device__ __forceinline__ void weight_producer_role(const uint4* __restrict__ w
           mbar_arrive(BAR(B_WFULL + ws));                    // timing experiment: no weight traffic
         } else {
           mbar_expect_tx(BAR(B_WFULL + ws), bytes);
-          bulk_g2s(sbase + SM_W + ws * W_STAGE_BYTES, src, bytes, BAR(B_WFULL + ws));
+          bulk_g2s(sbase + SM_W + ws * stage_bytes, src, bytes, BAR(B_WFULL + ws));
         }
         src += bytes;
         if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
@@ -601,7 +601,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
     }
   } else if (warp == 1) {
     // ================================================================ weight producer (1-D TMA bulk copies)
-    if (lane == 0) weight_producer_role(wtc, sbase, bar0, ncb, K, W_STEP_BYTES, TPS, ntiles, n_tq, n_cob);
+    if (lane == 0) weight_producer_role(wtc, sbase, bar0, ncb, K, W_STEP_BYTES, TPS, W_STAGE_BYTES, ntiles, n_tq, n_cob);
   } else if (warp < 2 + NUM_STAGERS / 32) {
     stager_role<MODE>(a, smem, sbase, bar0, ncb, RW, ntiles, n_tq, n_cob, tid, warp, lane);
   } else {
@@ -814,10 +814,17 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
 // channel-major kernel.  FAST recipe only.
 __host__ __device__ __forceinline__ int tmajor_nc(int Cout) { return Cout <= 16 ? 16 : ((Cout + 31) & ~31); }
 
-constexpr int SM_TSTAT = SM_EPI;                          // [2 tile parities][8 warps][128 channels][3] floats
-constexpr int SM_TBIAS = SM_TSTAT + 2 * 8 * 128 * 3 * 4;  // 128 floats
+// Shared memory of the time-major kernel: the weight ring uses 8 KB stages (the first half of the channel-major ring), the
+// second half and whatever the statistics scratch ([2 tile parities][8 warps][NC][3] floats) leaves of the epilogue area hold
+// the RESIDUAL RING: 2 KB slots (16 channels x 32 frames) filled by 4-byte cp.async copies, up to three steps ahead per warp.
+constexpr int T_WSTAGE = 8192;                            // bytes per weight stage: 8 taps (NC = 16) .. 1 tap (NC = 128)
+constexpr int SM_TRES_A = SM_W + W_STAGES * T_WSTAGE;     // 12 residual slots in the unused half of the weight ring
+constexpr int T_SLOT = 2048, T_SLOTS_A = (W_STAGES * (W_STAGE_BYTES - T_WSTAGE)) / T_SLOT;
+constexpr int SM_TBIAS = SM_EPI;                          // 128 floats
 constexpr int SM_TPILOT = SM_TBIAS + 512;                 // [8 warps][32] floats
-static_assert(SM_TPILOT + 8 * 32 * 4 <= SM_BAR, "time-major epilogue scratch");
+constexpr int SM_TSTAT = SM_TPILOT + 8 * 32 * 4;          // [2][8][NC][3] floats, then residual slots up to SM_BAR
+static_assert(SM_TSTAT + 2 * 8 * 128 * 3 * 4 <= SM_BAR, "time-major epilogue scratch");
+static_assert(T_SLOTS_A + (SM_BAR - SM_TSTAT - 2 * 8 * 128 * 3 * 4) / T_SLOT >= 16, "two residual steps per warp in flight for NC = 128");
 
 template <bool RES, int ACC>
 __device__ __forceinline__ void tct_rows(float (&v)[16], const float (&rv)[16], const float* bsm_c0, float* yp0, const unsigned ys,
@@ -850,6 +857,29 @@ __device__ __forceinline__ void tct_rows(float (&v)[16], const float (&rv)[16], 
   }
 }
 
+// Full step (16 existing channels, 32 existing frames, plain epilogue): no predicates, the output pointer advances row by row.
+template <bool RES, int ACC>
+__device__ __forceinline__ void tct_rows_full(float (&v)[16], const float (&rv)[16], const float* bsm_c0, float* yp0, const unsigned ys,
+                                              const float acc_div) {
+  float bb[16];
+#pragma unroll
+  for (int k4 = 0; k4 < 4; ++k4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bsm_c0 + 4 * k4);
+    bb[4 * k4] = b4.x; bb[4 * k4 + 1] = b4.y; bb[4 * k4 + 2] = b4.z; bb[4 * k4 + 3] = b4.w;
+  }
+  float* p = yp0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float val = v[j] * D_UNSCALE + bb[j];
+    if (RES) val += rv[j];
+    if (ACC == 1) val = *p + val;
+    if (ACC == 2) val = __fdiv_rn(*p + val, acc_div);
+    *p = val;
+    v[j] = val;
+    p += ys;
+  }
+}
+
 // One step of the transposing reduction: 2N values per lane -> N values per lane, each summed with the partner lane (lane ^ N).
 template <int N>
 __device__ __forceinline__ void xreduce_step(float* d, const int lane) {
@@ -872,15 +902,21 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + SM_BAR;
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * B_COUNT);
+  // accumulator ring: NBUF = 512 / (2 NC) buffers of two M blocks (2 for NC = 128 ... 8 for NC <= 32): the MMAs run up to
+  // NBUF tiles ahead of the epilogue, whose steps wait for residual rows from HBM
+  constexpr int T_TFULL = 16, T_TEMPTY = 24, T_MAXBUF = 8;
+  const int NBUF = min(T_MAXBUF, 512 / (2 * NC));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * 32);
 
   if (tid == 0) {
     for (int i = 0; i < W_STAGES; ++i) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(BAR(B_AFULL + i), NUM_STAGERS);
       mbar_init(BAR(B_AEMPTY + i), 1);
-      mbar_init(BAR(B_TFULL + i), 1);
-      mbar_init(BAR(B_TEMPTY + i), NUM_EPI);
+    }
+    for (int i = 0; i < T_MAXBUF; ++i) {
+      mbar_init(BAR(T_TFULL + i), 1);
+      mbar_init(BAR(T_TEMPTY + i), NUM_EPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -894,7 +930,7 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
   const uint32_t tmem_base = *tmem_slot;
   const int K = a.K;
   const int wstep = 64 * NC;                      // bytes of one (16 channels, tap) step: 2 planes x 2 chunks x NC rows x 16 B
-  const int tps = W_STAGE_BYTES / wstep;          // taps per weight stage: 2 (NC = 128) .. 16 (NC = 16)
+  const int tps = T_WSTAGE / wstep;               // taps per weight stage: 1 (NC = 128, 96) .. 8 (NC = 16)
 
   if (warp == 0) {
     // ================================================================ MMA issuer (converged warp, one elected lane)
@@ -903,10 +939,9 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
     const uint64_t dx_d = make_desc(sbase + SM_ACT, (uint32_t)RWP * 16, 128), dw_d = make_desc(sbase + SM_W, (uint32_t)NC * 16, 128);
     const uint32_t dx_lo0 = (uint32_t)dx_d, dx_hi = (uint32_t)(dx_d >> 32), dw_lo0 = (uint32_t)dw_d, dw_hi = (uint32_t)(dw_d >> 32);
     const uint32_t dil_ = (uint32_t)a.dil, wplane16 = (uint32_t)(2 * NC), wstep16 = (uint32_t)(4 * NC);
-    int ws = 0, wph = 0, as = 0, aph = 0, it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      mbar_wait(BAR(B_TEMPTY + buf), ((it >> 1) & 1) ^ 1);
+    int ws = 0, wph = 0, as = 0, aph = 0, buf = 0, tph = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      mbar_wait(BAR(T_TEMPTY + buf), tph ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(buf * 2 * NC);   // M block 0; M block 1 at + NC columns
       uint32_t acc = 0;
@@ -919,7 +954,7 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
           tc_fence_after();
           const int nt = min(tps, K - tap0);
           if (elected) {
-            uint32_t w_lo = dw_lo0 + (uint32_t)ws * (W_STAGE_BYTES >> 4);
+            uint32_t w_lo = dw_lo0 + (uint32_t)ws * (T_WSTAGE >> 4);
             for (int t = 0; t < nt; ++t) {
 #pragma unroll
               for (int m = 0; m < 2; ++m) {
@@ -940,18 +975,23 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
         if (elected) tc_commit(BAR(B_AEMPTY + as));
         if (++as == 2) { as = 0; aph ^= 1; }
       }
-      if (elected) tc_commit(BAR(B_TFULL + buf));
+      if (elected) tc_commit(BAR(T_TFULL + buf));
+      if (++buf == NBUF) { buf = 0; tph ^= 1; }
     }
   } else if (warp == 1) {
     // ================================================================ weight producer (1-D TMA bulk copies)
-    if (lane == 0) weight_producer_role(wtc, sbase, bar0, ncb, K, wstep, tps, ntiles, n_tq, 1);
+    if (lane == 0) weight_producer_role(wtc, sbase, bar0, ncb, K, wstep, tps, T_WSTAGE, ntiles, n_tq, 1);
   } else if (warp < 2 + NUM_STAGERS / 32) {
     stager_role<MODE>(a, smem, sbase, bar0, ncb, RW, ntiles, n_tq, 1, tid, warp, lane);
   } else {
     // ================================================================ epilogue (8 warps): warp -> (M block, 32 frames)
-    // The work of a warp is the sequence of (tile, 16-channel group) steps of its frames.  The residual values of step s+1
-    // are loaded (16 registers, one 128-byte row piece per warp instruction) before step s is processed -- across tile
-    // boundaries too -- so their latency hides behind one step of TMEM load, stores and statistics.
+    // The work of a warp is the sequence of (tile, 16-channel group) steps of its frames.  The residual values of a step
+    // travel HBM -> shared memory as 4-byte cp.async copies (each lane copies and later reads its own frame of 16 rows: one
+    // 128-byte row piece per warp instruction, no registers held while in flight) issued D = 2 or 3 steps ahead -- across
+    // tile boundaries -- so 32-48 KB of residual rows are in flight per SM while the accumulator ring lets the MMAs run ahead.
+    // A ring slot is [16 channels][32 frames] floats with the 16-byte chunks of a row XOR-swizzled by (channel & 7): the
+    // finished values of a step go back into the slot the residuals came from (same word per lane), and the InstanceNorm
+    // partials read it TRANSPOSED -- lane = (channel, half of the frames), four conflict-free 128-bit loads.
     const int ewi = warp - (2 + NUM_STAGERS / 32);  // 0..7
     const int q = warp & 3;                          // TMEM lane quarter this warp may access = frames 32q .. 32q+31 of the M block
     const int m = ewi >> 2;                          // M block (which 128 frames of the tile)
@@ -963,107 +1003,188 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
     const int ytst_ = a.y_tstride, ytoff_ = a.y_toffset, rshift_ = a.res_shift;
     const float out_div_ = a.out_div, acc_div_ = a.accum_div;
     const bool has_stats = a.stats != nullptr, has_res = a.res != nullptr;
+    const bool plain = (out_div_ == 1.0f) && (out_act_ == ST2_ACT_NONE);
     const int ng = NC >> 4;                          // 16-channel groups per tile
     const int fr0 = m * 128 + q * 32;                // first frame of this warp within a tile
+    const int tl = fr0 + lane;                       // this lane's frame within a tile
+    // residual ring: slots 0 .. T_SLOTS_A-1 behind the weight ring, the others behind the statistics scratch
+    const int res_b0 = SM_TSTAT + 2 * 8 * NC * 3 * 4;
+    const int D = min(3, (T_SLOTS_A + (SM_BAR - res_b0) / T_SLOT) / 8);      // steps ahead (>= 2, see static_assert)
+    auto slot_base = [&](int p) -> uint32_t {
+      const int k = p * 8 + ewi;
+      return sbase + (uint32_t)(k < T_SLOTS_A ? SM_TRES_A + k * T_SLOT : res_b0 + (k - T_SLOTS_A) * T_SLOT);
+    };
+    // byte offset of (channel j, this lane's frame) inside a slot: row j, chunk (lane / 4) ^ (j & 7), word lane & 3
+    uint32_t swz[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) swz[k] = (uint32_t)((((lane >> 2) ^ k) << 4) | ((lane & 3) << 2));
+    // transposed view for the statistics: lane -> channel lane / 2, frames 16 * (lane & 1) .. + 15 (four 16-byte chunks)
+    const int sch = lane >> 1, shalf = lane & 1;
+    uint32_t tsw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tsw[k] = (uint32_t)(sch * 128 + ((((shalf << 2) | k) ^ (sch & 7)) << 4));
     if (et < 128) bsm[et] = (a.bias && et < Cout_) ? a.bias[et] : 0.f;
     asm volatile("bar.sync 5, %0;" ::"n"(NUM_EPI));
-    float rvn[16];
+    // request the residual values of the step `ahead` steps after (tile_, gi_) into ring position p (one commit group per step,
+    // also when there is nothing to copy, so that the group count identifies the step)
+    auto issue = [&](int tile_, int gi_, int ahead, int p) {
+      if (has_res) {
+        const int s_ = gi_ + ahead;
+        const int dt = s_ / ng;
+        const int gi = s_ - dt * ng;
+        tile_ += dt * (int)gridDim.x;
+        if (tile_ < ntiles) {
+          const int tq_ = tile_ % n_tq, b_ = tile_ / n_tq;
+          const int ncols_ = min(TN, Lq_ - tq_ * TN);
+          const int oidx_ = (tq_ * TN + tl) * ytst_ + ytoff_;
+          const float* r0 = a.res + (long long)b_ * a.res_bstride + (long long)(gi * 16) * res_len_ + (oidx_ >> rshift_);
+          const uint32_t dst = slot_base(p);
+          if (ncols_ - fr0 >= 32 && gi * 16 + 16 <= Cout_) {   // warp-uniform: full step
 #pragma unroll
-    for (int j = 0; j < 16; ++j) rvn[j] = 0.f;
-    // residual values of group gi of tile `tile_` -> rvn (zeros where the frame or the channel does not exist)
-    auto prefetch = [&](int tile_, int gi) {
-      if (has_res && tile_ < ntiles) {
-        const int tq_ = tile_ % n_tq, b_ = tile_ / n_tq;
-        const int tl_ = fr0 + lane;
-        const bool tv_ = tl_ < min(TN, Lq_ - tq_ * TN);
-        const int oidx_ = (tq_ * TN + tl_) * ytst_ + ytoff_;
-        const float* r0 = a.res + (long long)b_ * a.res_bstride + (long long)(gi * 16) * res_len_ + (oidx_ >> rshift_);
+            for (int j = 0; j < 16; ++j) {
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * j + swz[j & 7]), "l"(r0) : "memory");
+              r0 += (unsigned)res_len_;
+            }
+          } else if (tl < ncols_) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) rvn[j] = (tv_ && (gi * 16 + j) < Cout_) ? __ldg(r0 + (unsigned)j * (unsigned)res_len_) : 0.f;
+            for (int j = 0; j < 16; ++j) {
+              if (gi * 16 + j < Cout_)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * j + swz[j & 7]), "l"(r0 + (unsigned)j * (unsigned)res_len_) : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
     };
-    prefetch(blockIdx.x, 0);
-    int it = 0;
+    for (int p = 0; p < D; ++p) issue(blockIdx.x, 0, p, p);
+    int it = 0, buf = 0, tph = 0, rp = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int tq = tile % n_tq, b = tile / n_tq;
-      const int buf = it & 1;
-      const int t0 = tq * TN;
-      const int ncols = min(TN, Lq_ - t0);
-      const int tl = fr0 + lane;                       // frame within the tile
+      const int ncols = min(TN, Lq_ - tq * TN);
       const bool tv = tl < ncols;
       const int nvalid = max(0, min(32, ncols - fr0));   // warp-uniform
-      const int oidx = (t0 + tl) * ytst_ + ytoff_;
-      float* yp = a.y + (long long)b * a.y_bstride + oidx;
-      float* sst = sstat + ((it & 1) * 8 + ewi) * 128 * 3;
+      float* yp = a.y + (long long)b * a.y_bstride + ((tq * TN + tl) * ytst_ + ytoff_);
+      float* sst = sstat + ((it & 1) * 8 + ewi) * NC * 3;
+      mbar_wait(BAR(T_TFULL + buf), tph);
+      tc_fence_after();
       for (int gi = 0; gi < ng; ++gi) {
         const int c0 = gi * 16;
-        float rv[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) rv[j] = rvn[j];
-        if (gi + 1 < ng) prefetch(tile, gi + 1);
-        else prefetch(tile + gridDim.x, 0);
-        if (gi == 0) {
-          mbar_wait(BAR(B_TFULL + buf), (it >> 1) & 1);
-          tc_fence_after();
-        }
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * NC + m * NC + c0), v);
-        if (gi + 1 == ng) {   // last group: the accumulator is free for the MMAs of the tile after next
+        if (gi + 1 == ng) {   // last group: the accumulator buffer is free again
           tc_fence_before();
-          mbar_arrive(BAR(B_TEMPTY + buf));
+          mbar_arrive(BAR(T_TEMPTY + buf));
         }
         const int nch = min(16, Cout_ - c0);   // warp-uniform, may be <= 0 for padded channel groups
-        if (nch <= 0 || nvalid == 0) continue;
+        const bool full = (nch == 16) && (nvalid == 32) && plain;   // warp-uniform
+        const uint32_t slot = slot_base(rp);
+        float rv[16];
+        if (has_res) {
+          // this step's copies have landed when at most D-1 newer groups are pending
+          if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+          else asm volatile("cp.async.wait_group 1;" ::: "memory");
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rv[j]) : "r"(slot + 128u * j + swz[j & 7]) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float r = 0.f;
+              if (tv && j < nch) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(slot + 128u * j + swz[j & 7]) : "memory");
+              rv[j] = r;
+            }
+          }
+        }
         float* yp0 = yp + (long long)c0 * y_len_;
         const float* bs0 = bsm + c0;
         const unsigned ys = (unsigned)y_len_;
-        if (has_res) {
-          if (acc_ == 0) tct_rows<true, 0>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-          else if (acc_ == 1) tct_rows<true, 1>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-          else tct_rows<true, 2>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-        } else {
-          if (acc_ == 0) tct_rows<false, 0>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-          else if (acc_ == 1) tct_rows<false, 1>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-          else tct_rows<false, 2>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-        }
-        if (has_stats) {
-          // pilot sample per channel = the value of the warp's first frame (always valid when nvalid > 0)
-          if (lane == 0) {
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4)
-              *reinterpret_cast<float4*>(&pil[4 * k4]) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+        if (full) {
+          if (has_res) {
+            if (acc_ == 0) tct_rows_full<true, 0>(v, rv, bs0, yp0, ys, acc_div_);
+            else if (acc_ == 1) tct_rows_full<true, 1>(v, rv, bs0, yp0, ys, acc_div_);
+            else tct_rows_full<true, 2>(v, rv, bs0, yp0, ys, acc_div_);
+          } else {
+            if (acc_ == 0) tct_rows_full<false, 0>(v, rv, bs0, yp0, ys, acc_div_);
+            else if (acc_ == 1) tct_rows_full<false, 1>(v, rv, bs0, yp0, ys, acc_div_);
+            else tct_rows_full<false, 2>(v, rv, bs0, yp0, ys, acc_div_);
           }
-          __syncwarp();
+          if (has_stats) {
+            // values back into the slot (each lane overwrites the words its residuals came from), read transposed
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const float4 p4 = *reinterpret_cast<const float4*>(&pil[4 * k4]);
-            v[4 * k4] = tv ? v[4 * k4] - p4.x : 0.f;
-            v[4 * k4 + 1] = tv ? v[4 * k4 + 1] - p4.y : 0.f;
-            v[4 * k4 + 2] = tv ? v[4 * k4 + 2] - p4.z : 0.f;
-            v[4 * k4 + 3] = tv ? v[4 * k4 + 3] - p4.w : 0.f;
-          }
-          {  // lanes L and L^16 hold the same 16 channels: the lower lane continues with the sums, the upper one with the squares
-            const bool up = (lane & 16) != 0;
+            for (int j = 0; j < 16; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + 128u * j + swz[j & 7]), "f"(v[j]) : "memory");
+            __syncwarp();
+            float x[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float o = __shfl_xor_sync(0xffffffffu, v[i], 16);
-              v[i] = up ? fmaf(v[i], v[i], o * o) : v[i] + o;
+            for (int k = 0; k < 4; ++k)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4 * k]), "=f"(x[4 * k + 1]), "=f"(x[4 * k + 2]), "=f"(x[4 * k + 3]) : "r"(slot + tsw[k]) : "memory");
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) sum += x[k];
+            const float mh = sum * (1.0f / 16.0f);
+            float qh = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { const float d = x[k] - mh; qh = fmaf(d, d, qh); }
+            // the two halves of a channel sit in neighbouring lanes: Chan merge of two 16-sample records
+            const float mo = __shfl_xor_sync(0xffffffffu, mh, 1), qo = __shfl_xor_sync(0xffffffffu, qh, 1);
+            const float dl = mo - mh;
+            if (shalf == 0) {
+              float* sp = sst + (c0 + sch) * 3;
+              sp[0] = 32.0f; sp[1] = mh + 0.5f * dl; sp[2] = qh + qo + dl * dl * 8.0f;
             }
+            __syncwarp();   // every lane has read the slot: it may be refilled
           }
-          xreduce_step<8>(v, lane);
-          xreduce_step<4>(v, lane);
-          xreduce_step<2>(v, lane);
-          xreduce_step<1>(v, lane);
-          // lane L < 16: S1 (sum of deviations from the pilot) of channel c0 + L; lane 16 + L: S2 (sum of their squares)
-          const float s2 = __shfl_down_sync(0xffffffffu, v[0], 16);
-          const float nn = (float)nvalid;
-          const float pl = pil[lane & 15];
-          if (lane < nch) {
-            float* sp = sst + (c0 + lane) * 3;
-            sp[0] = nn; sp[1] = pl + v[0] / nn; sp[2] = fmaxf(0.f, s2 - v[0] * v[0] / nn);
+        } else if (nch > 0 && nvalid > 0) {
+          if (has_res) {
+            if (acc_ == 0) tct_rows<true, 0>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+            else if (acc_ == 1) tct_rows<true, 1>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+            else tct_rows<true, 2>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+          } else {
+            if (acc_ == 0) tct_rows<false, 0>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+            else if (acc_ == 1) tct_rows<false, 1>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+            else tct_rows<false, 2>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
           }
-          __syncwarp();
+          if (has_stats) {
+            // partial step (tail tile / channel tail / output activation): transposing shuffle tree over the valid frames,
+            // deviations from a pilot sample per channel = the value of the warp's first frame (valid when nvalid > 0)
+            if (lane == 0) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4)
+                *reinterpret_cast<float4*>(&pil[4 * k4]) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const float4 p4 = *reinterpret_cast<const float4*>(&pil[4 * k4]);
+              v[4 * k4] = tv ? v[4 * k4] - p4.x : 0.f;
+              v[4 * k4 + 1] = tv ? v[4 * k4 + 1] - p4.y : 0.f;
+              v[4 * k4 + 2] = tv ? v[4 * k4 + 2] - p4.z : 0.f;
+              v[4 * k4 + 3] = tv ? v[4 * k4 + 3] - p4.w : 0.f;
+            }
+            {  // lanes L and L^16 hold the same 16 channels: the lower lane continues with the sums, the upper one with the squares
+              const bool up = (lane & 16) != 0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float o = __shfl_xor_sync(0xffffffffu, v[i], 16);
+                v[i] = up ? fmaf(v[i], v[i], o * o) : v[i] + o;
+              }
+            }
+            xreduce_step<8>(v, lane);
+            xreduce_step<4>(v, lane);
+            xreduce_step<2>(v, lane);
+            xreduce_step<1>(v, lane);
+            // lane L < 16: S1 (sum of deviations from the pilot) of channel c0 + L; lane 16 + L: S2 (sum of their squares)
+            const float s2 = __shfl_down_sync(0xffffffffu, v[0], 16);
+            const float nn = (float)nvalid;
+            const float pl = pil[lane & 15];
+            if (lane < nch) {
+              float* sp = sst + (c0 + lane) * 3;
+              sp[0] = nn; sp[1] = pl + v[0] / nn; sp[2] = fmaxf(0.f, s2 - v[0] * v[0] / nn);
+            }
+            __syncwarp();
+          }
         }
+        issue(tile, gi, D, rp);   // the slot is free again: the step D steps ahead
+        if (++rp == D) rp = 0;
       }
       if (has_stats) {
         if (nvalid == 0) {   // this warp's frames are beyond the row: empty records for every channel
@@ -1076,7 +1197,7 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
           float n = 0.f, mean = 0.f, m2 = 0.f;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) {
-            const float* sp = sstat + (((it & 1) * 8 + m * 4 + qq) * 128 + co) * 3;
+            const float* sp = sstat + (((it & 1) * 8 + m * 4 + qq) * NC + co) * 3;
             const float nb = sp[0], mb = sp[1], qb = sp[2];
             if (nb > 0.f) {
               const float nn = n + nb, dl = mb - mean;
@@ -1089,7 +1210,9 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
           gp[0] = n; gp[1] = mean; gp[2] = m2;
         }
       }
+      if (++buf == NBUF) { buf = 0; tph ^= 1; }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
