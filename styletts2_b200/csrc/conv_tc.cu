@@ -338,37 +338,53 @@ __device__ __forceinline__ void stager_role(const st2_conv_args& a, uint8_t* sme
   const float* x_al = reinterpret_cast<const float*>((uintptr_t)a.x & ~(uintptr_t)15);
   // issue mapping: thread -> one channel of the block and every ST_PER_CH-th 16-byte chunk of its row
   const int ich = st / ST_PER_CH, iq0 = st - ich * ST_PER_CH;
-  int i_tile = -1, i_g0 = 0;  // producer-side tile state (runs RAW_STAGES-1 blocks ahead of the conversion)
+  // producer-side state (runs RAW_STAGES-1 blocks ahead of the conversion); issue() is called for g = 0, 1, 2, ... in order,
+  // so (tile, channel block, ring slot) advance by counters instead of divisions
+  int i_tl = 0, i_cb = 0, i_slot = 0, i_g0 = 0;
+  bool i_inter = false;
   long long i_boff = 0;
   const int dbg_i = g_dbg;
   auto issue = [&](int g) {
     if (g < total_blocks && !(dbg_i & 32)) {
-      const int tl = g / ncb, cb = g - tl * ncb;
-      if (tl != i_tile) {
-        i_tile = tl;
-        const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
+      if (i_cb == 0) {
+        const TileCoord tc_ = tile_coord(blockIdx.x + i_tl * gridDim.x, n_tq, n_cob);
         i_boff = (long long)tc_.b * a.x_bstride;
         i_g0 = tc_.tq * TN - a.pad;
+        i_inter = (i_g0 >= 0) && (i_g0 + RW <= Lin_);   // the whole window lies inside the rows
       }
-      const int c = cb * CB + ich;
+      const int c = i_cb * CB + ich;
       const long long e0 = i_boff + (long long)min(c, Cin_ - 1) * Lin_ + i_g0;   // first window element, floats from a.x
-      const int shift = (int)((xaddr4 + (unsigned long long)e0) & 3ull);
-      const int rlo = max(0, -i_g0), rhi = min(RW, Lin_ - i_g0);              // rows [rlo, rhi) are inside the tensor
-      int qlo = 0, qhi = 0;
-      if (c < Cin_ && rhi > rlo) { qlo = (rlo + shift) >> 2; qhi = (rhi + shift + 3) >> 2; }
+      const int shift = (int)(((unsigned)xaddr4 + (unsigned)e0) & 3u);
       const long long w0 = e0 - shift;                                          // aligned window start, floats from a.x
       const float* src0 = a.x + w0;
       const long long end_rel = tensor_end - w0;
-      uint32_t dst = sbase + SM_RAW + (g % RAW_STAGES) * RAW_BYTES + (uint32_t)(ich * RAW_PITCH + iq0 * 4) * 4;
+      uint32_t dst = sbase + SM_RAW + i_slot * RAW_BYTES + (uint32_t)(ich * RAW_PITCH + iq0 * 4) * 4;
+      if (i_inter && c < Cin_ && end_rel >= (long long)(RW + 8)) {
+        // interior window of an existing channel, every chunk entirely inside the tensor: only the chunk count matters
+        const int qhi = (RW + shift + 3) >> 2;
+        const float* src = src0 + 4 * iq0;
 #pragma unroll
-      for (int i = 0; i < RAW_CHUNKS / ST_PER_CH; ++i) {
-        const int q = iq0 + ST_PER_CH * i;
-        const bool ok = (q >= qlo) && (q < qhi);
-        const long long rem = end_rel - 4ll * q;
-        const int nbytes = ok ? (rem >= 4 ? 16 : (int)rem * 4) : 0;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src0 + 4 * q : x_al), "r"(nbytes) : "memory");
-        dst += ST_PER_CH * 16;
+        for (int i = 0; i < RAW_CHUNKS / ST_PER_CH; ++i) {
+          const bool ok = (iq0 + ST_PER_CH * i) < qhi;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + i * ST_PER_CH * 16), "l"(ok ? src + 4 * ST_PER_CH * i : x_al),
+                       "r"(ok ? 16 : 0) : "memory");
+        }
+      } else {
+        const int rlo = max(0, -i_g0), rhi = min(RW, Lin_ - i_g0);              // rows [rlo, rhi) are inside the tensor
+        int qlo = 0, qhi = 0;
+        if (c < Cin_ && rhi > rlo) { qlo = (rlo + shift) >> 2; qhi = (rhi + shift + 3) >> 2; }
+#pragma unroll
+        for (int i = 0; i < RAW_CHUNKS / ST_PER_CH; ++i) {
+          const int q = iq0 + ST_PER_CH * i;
+          const bool ok = (q >= qlo) && (q < qhi);
+          const long long rem = end_rel - 4ll * q;
+          const int nbytes = ok ? (rem >= 4 ? 16 : (int)rem * 4) : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src0 + 4 * q : x_al), "r"(nbytes) : "memory");
+          dst += ST_PER_CH * 16;
+        }
       }
+      if (++i_cb == ncb) { i_cb = 0; ++i_tl; }
+      if (++i_slot == RAW_STAGES) i_slot = 0;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -383,14 +399,16 @@ __device__ __forceinline__ void stager_role(const st2_conv_args& a, uint8_t* sme
   const int kc = sw & 1, rg = (sw >> 1) * 32 + lane;
   constexpr int NRC = (RW_MAX + ROWS_PER_PASS - 1) / ROWS_PER_PASS;
   const float xs_ = X_SCALE;
+  int cb = 0, c_slot = 0;
+  unsigned c_row0 = 0;   // low 32 bits of the element index of (tile's utterance, channel 0, first window frame): only its 4-byte phase is used
   for (int g = 0; g < total_blocks; ++g) {
-    const int tl = g / ncb, cb = g - tl * ncb;
-    if (tl != c_tile) {
-      c_tile = tl;
-      const TileCoord tc_ = tile_coord(blockIdx.x + tl * gridDim.x, n_tq, n_cob);
+    if (cb == 0) {
+      ++c_tile;
+      const TileCoord tc_ = tile_coord(blockIdx.x + c_tile * gridDim.x, n_tq, n_cob);
       c_b = tc_.b;
       c_boff = (long long)tc_.b * a.x_bstride;
       c_g0 = tc_.tq * TN - a.pad;
+      c_row0 = (unsigned)xaddr4 + (unsigned)c_boff + (unsigned)c_g0;
     }
     asm volatile("cp.async.wait_group %0;" ::"n"(RAW_STAGES - 2) : "memory");
     asm volatile("bar.sync 1, %0;" ::"n"(NUM_STAGERS));  // block g landed for everybody; block g-1 fully converted
@@ -415,7 +433,7 @@ __device__ __forceinline__ void stager_role(const st2_conv_args& a, uint8_t* sme
     float pa[8], pb[8], al[8], ia[8];
     int sh[8];
     {
-      const int sh0 = (int)((xaddr4 + (unsigned long long)(c_boff + (long long)c0 * Lin_ + c_g0)) & 3ull), lin3 = Lin_ & 3;
+      const int sh0 = (int)((c_row0 + (unsigned)c0 * (unsigned)Lin_) & 3u), lin3 = Lin_ & 3;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         pa[j] = coef[c0 + j]; pb[j] = coef[CIN_PAD_MAX + c0 + j]; al[j] = coef[2 * CIN_PAD_MAX + c0 + j];
@@ -423,7 +441,7 @@ __device__ __forceinline__ void stager_role(const st2_conv_args& a, uint8_t* sme
         sh[j] = ((sh0 + j * lin3) & 3) + j * RAW_PITCH;   // 4-byte phase of channel c0+j's row start (padded channels: any)
       }
     }
-    const float* raw = reinterpret_cast<const float*>(smem + SM_RAW + (g % RAW_STAGES) * RAW_BYTES) + (kc * 8) * RAW_PITCH;
+    const float* raw = reinterpret_cast<const float*>(smem + SM_RAW + c_slot * RAW_BYTES) + (kc * 8) * RAW_PITCH;
     mbar_wait(BAR(B_AEMPTY + as), aph ^ 1);
     uint8_t* p0 = smem + SM_ACT + as * ACT_BUF_BYTES;
     uint8_t* p1 = p0 + ACT_PLANE_BYTES;
@@ -444,6 +462,8 @@ __device__ __forceinline__ void stager_role(const st2_conv_args& a, uint8_t* sme
     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     mbar_arrive(BAR(B_AFULL + as));
     if (++as == 2) { as = 0; aph ^= 1; }
+    if (++cb == ncb) cb = 0;
+    if (++c_slot == RAW_STAGES) c_slot = 0;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -858,9 +878,10 @@ __device__ __forceinline__ void tct_rows(float (&v)[16], const float (&rv)[16], 
 }
 
 // Full step (16 existing channels, 32 existing frames, plain epilogue): no predicates, the output pointer advances row by row.
+// yo = the 16 values of y to accumulate into (ACC != 0), loaded one step ahead by the caller.
 template <bool RES, int ACC>
-__device__ __forceinline__ void tct_rows_full(float (&v)[16], const float (&rv)[16], const float* bsm_c0, float* yp0, const unsigned ys,
-                                              const float acc_div) {
+__device__ __forceinline__ void tct_rows_full(float (&v)[16], const float (&rv)[16], const float (&yo)[16], const float* bsm_c0, float* yp0,
+                                              const unsigned ys, const float acc_div) {
   float bb[16];
 #pragma unroll
   for (int k4 = 0; k4 < 4; ++k4) {
@@ -872,8 +893,8 @@ __device__ __forceinline__ void tct_rows_full(float (&v)[16], const float (&rv)[
   for (int j = 0; j < 16; ++j) {
     float val = v[j] * D_UNSCALE + bb[j];
     if (RES) val += rv[j];
-    if (ACC == 1) val = *p + val;
-    if (ACC == 2) val = __fdiv_rn(*p + val, acc_div);
+    if (ACC == 1) val = yo[j] + val;
+    if (ACC == 2) val = __fdiv_rn(yo[j] + val, acc_div);
     *p = val;
     v[j] = val;
     p += ys;
@@ -892,6 +913,276 @@ __device__ __forceinline__ void xreduce_step(float* d, const int lane) {
   }
 }
 
+constexpr int T_TFULL = 16, T_TEMPTY = 24, T_MAXBUF = 8;   // barrier slots of the accumulator ring (time-major kernel)
+
+// Epilogue role of the time-major kernel.  HAS_ACC: the launch accumulates into y (MRF sum, accum_mode != 0): the y values of a
+// full step are loaded one step ahead into registers (a read at the point of use would expose the HBM latency 16 times per step).
+template <bool HAS_ACC>
+__device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_t* smem, const uint32_t sbase, const uint32_t bar0,
+                                                  const uint32_t tmem_base, const int ntiles, const int n_tq, const int NC, const int NBUF,
+                                                  const int tid, const int warp, const int lane) {
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  // ================================================================ epilogue (8 warps): warp -> (M block, 32 frames)
+  // The work of a warp is the sequence of (tile, 16-channel group) steps of its frames.  The residual values of a step
+  // travel HBM -> shared memory as 4-byte cp.async copies (each lane copies and later reads its own frame of 16 rows: one
+  // 128-byte row piece per warp instruction, no registers held while in flight) issued D = 2 or 3 steps ahead -- across
+  // tile boundaries -- so 32-48 KB of residual rows are in flight per SM while the accumulator ring lets the MMAs run ahead.
+  // A ring slot is [16 channels][32 frames] floats with the 16-byte chunks of a row XOR-swizzled by (channel & 7): the
+  // finished values of a step go back into the slot the residuals came from (same word per lane), and the InstanceNorm
+  // partials read it TRANSPOSED -- lane = (channel, half of the frames), four conflict-free 128-bit loads.
+  const int ewi = warp - (2 + NUM_STAGERS / 32);  // 0..7
+  const int q = warp & 3;                          // TMEM lane quarter this warp may access = frames 32q .. 32q+31 of the M block
+  const int m = ewi >> 2;                          // M block (which 128 frames of the tile)
+  const int et = tid - (64 + NUM_STAGERS);         // 0..255
+  float* sstat = reinterpret_cast<float*>(smem + SM_TSTAT);
+  float* bsm = reinterpret_cast<float*>(smem + SM_TBIAS);
+  float* pil = reinterpret_cast<float*>(smem + SM_TPILOT) + ewi * 32;
+  const int y_len_ = a.y_len, res_len_ = a.res_len, acc_ = a.accum_mode, out_act_ = a.out_act, Cout_ = a.Cout, Lq_ = a.Lq;
+  const int ytst_ = a.y_tstride, ytoff_ = a.y_toffset, rshift_ = a.res_shift;
+  const float out_div_ = a.out_div, acc_div_ = a.accum_div;
+  const bool has_stats = a.stats != nullptr, has_res = a.res != nullptr;
+  const bool plain = (out_div_ == 1.0f) && (out_act_ == ST2_ACT_NONE);
+  const int ng = NC >> 4;                          // 16-channel groups per tile
+  const int fr0 = m * 128 + q * 32;                // first frame of this warp within a tile
+  const int tl = fr0 + lane;                       // this lane's frame within a tile
+  // residual ring: slots 0 .. T_SLOTS_A-1 behind the weight ring, the others behind the statistics scratch
+  const int res_b0 = SM_TSTAT + 2 * 8 * NC * 3 * 4;
+  const int D = min(3, (T_SLOTS_A + (SM_BAR - res_b0) / T_SLOT) / 8);      // steps ahead (>= 2, see static_assert)
+  auto slot_base = [&](int p) -> uint32_t {
+    const int k = p * 8 + ewi;
+    return sbase + (uint32_t)(k < T_SLOTS_A ? SM_TRES_A + k * T_SLOT : res_b0 + (k - T_SLOTS_A) * T_SLOT);
+  };
+  // byte offset of (channel j, this lane's frame) inside a slot: row j, chunk (lane / 4) ^ (j & 7), word lane & 3
+  uint32_t swz[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) swz[k] = (uint32_t)((((lane >> 2) ^ k) << 4) | ((lane & 3) << 2));
+  // transposed view for the statistics: lane -> channel lane / 2, frames 16 * (lane & 1) .. + 15 (four 16-byte chunks)
+  const int sch = lane >> 1, shalf = lane & 1;
+  uint32_t tsw[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) tsw[k] = (uint32_t)(sch * 128 + ((((shalf << 2) | k) ^ (sch & 7)) << 4));
+  if (et < 128) bsm[et] = (a.bias && et < Cout_) ? a.bias[et] : 0.f;
+  asm volatile("bar.sync 5, %0;" ::"n"(NUM_EPI));
+  // request the residual values of the step `ahead` steps after (tile_, gi_) into ring position p (one commit group per step,
+  // also when there is nothing to copy, so that the group count identifies the step)
+  auto issue = [&](int tile_, int gi_, int ahead, int p) {
+    if (has_res) {
+      const int s_ = gi_ + ahead;
+      const int dt = s_ / ng;
+      const int gi = s_ - dt * ng;
+      tile_ += dt * (int)gridDim.x;
+      if (tile_ < ntiles) {
+        const int tq_ = tile_ % n_tq, b_ = tile_ / n_tq;
+        const int ncols_ = min(TN, Lq_ - tq_ * TN);
+        const int oidx_ = (tq_ * TN + tl) * ytst_ + ytoff_;
+        const float* r0 = a.res + (long long)b_ * a.res_bstride + (long long)(gi * 16) * res_len_ + (oidx_ >> rshift_);
+        const uint32_t dst = slot_base(p);
+        if (ncols_ - fr0 >= 32 && gi * 16 + 16 <= Cout_) {   // warp-uniform: full step
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * j + swz[j & 7]), "l"(r0) : "memory");
+            r0 += (unsigned)res_len_;
+          }
+        } else if (tl < ncols_) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (gi * 16 + j < Cout_)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * j + swz[j & 7]), "l"(r0 + (unsigned)j * (unsigned)res_len_) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  };
+  for (int p = 0; p < D; ++p) issue(blockIdx.x, 0, p, p);
+  // HAS_ACC: the y values of the NEXT step (zeros where the frame or channel does not exist), one step ahead in registers
+  float yon[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) yon[j] = 0.f;
+  auto load_y = [&](int tile_, int gi_, int ahead) {
+    if (HAS_ACC) {
+      const int s_ = gi_ + ahead;
+      const int dt = s_ / ng;
+      const int gi = s_ - dt * ng;
+      tile_ += dt * (int)gridDim.x;
+      if (tile_ < ntiles) {
+        const int tq_ = tile_ % n_tq, b_ = tile_ / n_tq;
+        const bool tv_ = tl < min(TN, Lq_ - tq_ * TN);
+        const float* y0 = a.y + (long long)b_ * a.y_bstride + (long long)(gi * 16) * y_len_ + ((tq_ * TN + tl) * ytst_ + ytoff_);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          yon[j] = (tv_ && gi * 16 + j < Cout_) ? *y0 : 0.f;
+          y0 += (unsigned)y_len_;
+        }
+      }
+    }
+  };
+  load_y(blockIdx.x, 0, 0);
+  int it = 0, buf = 0, tph = 0, rp = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int tq = tile % n_tq, b = tile / n_tq;
+    const int ncols = min(TN, Lq_ - tq * TN);
+    const bool tv = tl < ncols;
+    const int nvalid = max(0, min(32, ncols - fr0));   // warp-uniform
+    float* yp = a.y + (long long)b * a.y_bstride + ((tq * TN + tl) * ytst_ + ytoff_);
+    float* sst = sstat + ((it & 1) * 8 + ewi) * NC * 3;
+    mbar_wait(BAR(T_TFULL + buf), tph);
+    tc_fence_after();
+    for (int gi = 0; gi < ng; ++gi) {
+      const int c0 = gi * 16;
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * NC + m * NC + c0), v);
+      if (gi + 1 == ng) {   // last group: the accumulator buffer is free again
+        tc_fence_before();
+        mbar_arrive(BAR(T_TEMPTY + buf));
+      }
+      const int nch = min(16, Cout_ - c0);   // warp-uniform, may be <= 0 for padded channel groups
+      const bool full = (nch == 16) && (nvalid == 32) && plain;   // warp-uniform
+      const uint32_t slot = slot_base(rp);
+      float rv[16];
+      if (has_res) {
+        // this step's copies have landed when at most D-1 newer groups are pending
+        if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rv[j]) : "r"(slot + 128u * j + swz[j & 7]) : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float r = 0.f;
+            if (tv && j < nch) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(slot + 128u * j + swz[j & 7]) : "memory");
+            rv[j] = r;
+          }
+        }
+      }
+      float* yp0 = yp + (long long)c0 * y_len_;
+      const float* bs0 = bsm + c0;
+      const unsigned ys = (unsigned)y_len_;
+      if (full) {
+        if (HAS_ACC) {
+          if (has_res) {
+            if (acc_ == 1) tct_rows_full<true, 1>(v, rv, yon, bs0, yp0, ys, acc_div_);
+            else tct_rows_full<true, 2>(v, rv, yon, bs0, yp0, ys, acc_div_);
+          } else {
+            if (acc_ == 1) tct_rows_full<false, 1>(v, rv, yon, bs0, yp0, ys, acc_div_);
+            else tct_rows_full<false, 2>(v, rv, yon, bs0, yp0, ys, acc_div_);
+          }
+        } else {
+          if (has_res) tct_rows_full<true, 0>(v, rv, yon, bs0, yp0, ys, acc_div_);
+          else tct_rows_full<false, 0>(v, rv, yon, bs0, yp0, ys, acc_div_);
+        }
+        load_y(tile, gi, 1);   // (HAS_ACC) y of the next step: in flight during the statistics and the next step's TMEM load
+        if (has_stats) {
+          // values back into the slot (each lane overwrites the words its residuals came from), read transposed
+#pragma unroll
+          for (int j = 0; j < 16; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + 128u * j + swz[j & 7]), "f"(v[j]) : "memory");
+          __syncwarp();
+          float x[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4 * k]), "=f"(x[4 * k + 1]), "=f"(x[4 * k + 2]), "=f"(x[4 * k + 3]) : "r"(slot + tsw[k]) : "memory");
+          float sum = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) sum += x[k];
+          const float mh = sum * (1.0f / 16.0f);
+          float qh = 0.f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { const float d = x[k] - mh; qh = fmaf(d, d, qh); }
+          // the two halves of a channel sit in neighbouring lanes: Chan merge of two 16-sample records
+          const float mo = __shfl_xor_sync(0xffffffffu, mh, 1), qo = __shfl_xor_sync(0xffffffffu, qh, 1);
+          const float dl = mo - mh;
+          if (shalf == 0) {
+            float* sp = sst + (c0 + sch) * 3;
+            sp[0] = 32.0f; sp[1] = mh + 0.5f * dl; sp[2] = qh + qo + dl * dl * 8.0f;
+          }
+          __syncwarp();   // every lane has read the slot: it may be refilled
+        }
+      } else if (nch > 0 && nvalid > 0) {
+        if (has_res) {
+          if (acc_ == 0) tct_rows<true, 0>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+          else if (acc_ == 1) tct_rows<true, 1>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+          else tct_rows<true, 2>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+        } else {
+          if (acc_ == 0) tct_rows<false, 0>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+          else if (acc_ == 1) tct_rows<false, 1>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+          else tct_rows<false, 2>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
+        }
+        load_y(tile, gi, 1);
+        if (has_stats) {
+          // partial step (tail tile / channel tail / output activation): transposing shuffle tree over the valid frames,
+          // deviations from a pilot sample per channel = the value of the warp's first frame (valid when nvalid > 0)
+          if (lane == 0) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+              *reinterpret_cast<float4*>(&pil[4 * k4]) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 p4 = *reinterpret_cast<const float4*>(&pil[4 * k4]);
+            v[4 * k4] = tv ? v[4 * k4] - p4.x : 0.f;
+            v[4 * k4 + 1] = tv ? v[4 * k4 + 1] - p4.y : 0.f;
+            v[4 * k4 + 2] = tv ? v[4 * k4 + 2] - p4.z : 0.f;
+            v[4 * k4 + 3] = tv ? v[4 * k4 + 3] - p4.w : 0.f;
+          }
+          {  // lanes L and L^16 hold the same 16 channels: the lower lane continues with the sums, the upper one with the squares
+            const bool up = (lane & 16) != 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float o = __shfl_xor_sync(0xffffffffu, v[i], 16);
+              v[i] = up ? fmaf(v[i], v[i], o * o) : v[i] + o;
+            }
+          }
+          xreduce_step<8>(v, lane);
+          xreduce_step<4>(v, lane);
+          xreduce_step<2>(v, lane);
+          xreduce_step<1>(v, lane);
+          // lane L < 16: S1 (sum of deviations from the pilot) of channel c0 + L; lane 16 + L: S2 (sum of their squares)
+          const float s2 = __shfl_down_sync(0xffffffffu, v[0], 16);
+          const float nn = (float)nvalid;
+          const float pl = pil[lane & 15];
+          if (lane < nch) {
+            float* sp = sst + (c0 + lane) * 3;
+            sp[0] = nn; sp[1] = pl + v[0] / nn; sp[2] = fmaxf(0.f, s2 - v[0] * v[0] / nn);
+          }
+          __syncwarp();
+        }
+      } else {
+        load_y(tile, gi, 1);
+      }
+      issue(tile, gi, D, rp);   // the slot is free again: the step D steps ahead
+      if (++rp == D) rp = 0;
+    }
+    if (has_stats) {
+      if (nvalid == 0) {   // this warp's frames are beyond the row: empty records for every channel
+        for (int c = lane; c < Cout_; c += 32) { sst[c * 3] = 0.f; sst[c * 3 + 1] = 0.f; sst[c * 3 + 2] = 0.f; }
+      }
+      // the four warps of an M block merge their records in fixed order: one partial per (tile, M block, channel)
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + m) : "memory");
+      const int co = et & 127;
+      if (co < Cout_) {
+        float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const float* sp = sstat + (((it & 1) * 8 + m * 4 + qq) * NC + co) * 3;
+          const float nb = sp[0], mb = sp[1], qb = sp[2];
+          if (nb > 0.f) {
+            const float nn = n + nb, dl = mb - mean;
+            mean += dl * (nb / nn);
+            m2 += qb + dl * dl * (n * nb / nn);
+            n = nn;
+          }
+        }
+        float* gp = a.stats + (((long long)b * Cout_ + co) * a.stats_nparts + a.stats_part_offset + 2 * tq + m) * 3;
+        gp[0] = n; gp[1] = mean; gp[2] = m2;
+      }
+    }
+    if (++buf == NBUF) { buf = 0; tph ^= 1; }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int ncb, const int RW, const int ntiles, const int n_tq,
                   const int NC) {
@@ -904,7 +1195,6 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   // accumulator ring: NBUF = 512 / (2 NC) buffers of two M blocks (2 for NC = 128 ... 8 for NC <= 32): the MMAs run up to
   // NBUF tiles ahead of the epilogue, whose steps wait for residual rows from HBM
-  constexpr int T_TFULL = 16, T_TEMPTY = 24, T_MAXBUF = 8;
   const int NBUF = min(T_MAXBUF, 512 / (2 * NC));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * 32);
 
@@ -984,235 +1274,8 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
   } else if (warp < 2 + NUM_STAGERS / 32) {
     stager_role<MODE>(a, smem, sbase, bar0, ncb, RW, ntiles, n_tq, 1, tid, warp, lane);
   } else {
-    // ================================================================ epilogue (8 warps): warp -> (M block, 32 frames)
-    // The work of a warp is the sequence of (tile, 16-channel group) steps of its frames.  The residual values of a step
-    // travel HBM -> shared memory as 4-byte cp.async copies (each lane copies and later reads its own frame of 16 rows: one
-    // 128-byte row piece per warp instruction, no registers held while in flight) issued D = 2 or 3 steps ahead -- across
-    // tile boundaries -- so 32-48 KB of residual rows are in flight per SM while the accumulator ring lets the MMAs run ahead.
-    // A ring slot is [16 channels][32 frames] floats with the 16-byte chunks of a row XOR-swizzled by (channel & 7): the
-    // finished values of a step go back into the slot the residuals came from (same word per lane), and the InstanceNorm
-    // partials read it TRANSPOSED -- lane = (channel, half of the frames), four conflict-free 128-bit loads.
-    const int ewi = warp - (2 + NUM_STAGERS / 32);  // 0..7
-    const int q = warp & 3;                          // TMEM lane quarter this warp may access = frames 32q .. 32q+31 of the M block
-    const int m = ewi >> 2;                          // M block (which 128 frames of the tile)
-    const int et = tid - (64 + NUM_STAGERS);         // 0..255
-    float* sstat = reinterpret_cast<float*>(smem + SM_TSTAT);
-    float* bsm = reinterpret_cast<float*>(smem + SM_TBIAS);
-    float* pil = reinterpret_cast<float*>(smem + SM_TPILOT) + ewi * 32;
-    const int y_len_ = a.y_len, res_len_ = a.res_len, acc_ = a.accum_mode, out_act_ = a.out_act, Cout_ = a.Cout, Lq_ = a.Lq;
-    const int ytst_ = a.y_tstride, ytoff_ = a.y_toffset, rshift_ = a.res_shift;
-    const float out_div_ = a.out_div, acc_div_ = a.accum_div;
-    const bool has_stats = a.stats != nullptr, has_res = a.res != nullptr;
-    const bool plain = (out_div_ == 1.0f) && (out_act_ == ST2_ACT_NONE);
-    const int ng = NC >> 4;                          // 16-channel groups per tile
-    const int fr0 = m * 128 + q * 32;                // first frame of this warp within a tile
-    const int tl = fr0 + lane;                       // this lane's frame within a tile
-    // residual ring: slots 0 .. T_SLOTS_A-1 behind the weight ring, the others behind the statistics scratch
-    const int res_b0 = SM_TSTAT + 2 * 8 * NC * 3 * 4;
-    const int D = min(3, (T_SLOTS_A + (SM_BAR - res_b0) / T_SLOT) / 8);      // steps ahead (>= 2, see static_assert)
-    auto slot_base = [&](int p) -> uint32_t {
-      const int k = p * 8 + ewi;
-      return sbase + (uint32_t)(k < T_SLOTS_A ? SM_TRES_A + k * T_SLOT : res_b0 + (k - T_SLOTS_A) * T_SLOT);
-    };
-    // byte offset of (channel j, this lane's frame) inside a slot: row j, chunk (lane / 4) ^ (j & 7), word lane & 3
-    uint32_t swz[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) swz[k] = (uint32_t)((((lane >> 2) ^ k) << 4) | ((lane & 3) << 2));
-    // transposed view for the statistics: lane -> channel lane / 2, frames 16 * (lane & 1) .. + 15 (four 16-byte chunks)
-    const int sch = lane >> 1, shalf = lane & 1;
-    uint32_t tsw[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) tsw[k] = (uint32_t)(sch * 128 + ((((shalf << 2) | k) ^ (sch & 7)) << 4));
-    if (et < 128) bsm[et] = (a.bias && et < Cout_) ? a.bias[et] : 0.f;
-    asm volatile("bar.sync 5, %0;" ::"n"(NUM_EPI));
-    // request the residual values of the step `ahead` steps after (tile_, gi_) into ring position p (one commit group per step,
-    // also when there is nothing to copy, so that the group count identifies the step)
-    auto issue = [&](int tile_, int gi_, int ahead, int p) {
-      if (has_res) {
-        const int s_ = gi_ + ahead;
-        const int dt = s_ / ng;
-        const int gi = s_ - dt * ng;
-        tile_ += dt * (int)gridDim.x;
-        if (tile_ < ntiles) {
-          const int tq_ = tile_ % n_tq, b_ = tile_ / n_tq;
-          const int ncols_ = min(TN, Lq_ - tq_ * TN);
-          const int oidx_ = (tq_ * TN + tl) * ytst_ + ytoff_;
-          const float* r0 = a.res + (long long)b_ * a.res_bstride + (long long)(gi * 16) * res_len_ + (oidx_ >> rshift_);
-          const uint32_t dst = slot_base(p);
-          if (ncols_ - fr0 >= 32 && gi * 16 + 16 <= Cout_) {   // warp-uniform: full step
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * j + swz[j & 7]), "l"(r0) : "memory");
-              r0 += (unsigned)res_len_;
-            }
-          } else if (tl < ncols_) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (gi * 16 + j < Cout_)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * j + swz[j & 7]), "l"(r0 + (unsigned)j * (unsigned)res_len_) : "memory");
-            }
-          }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-    };
-    for (int p = 0; p < D; ++p) issue(blockIdx.x, 0, p, p);
-    int it = 0, buf = 0, tph = 0, rp = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int tq = tile % n_tq, b = tile / n_tq;
-      const int ncols = min(TN, Lq_ - tq * TN);
-      const bool tv = tl < ncols;
-      const int nvalid = max(0, min(32, ncols - fr0));   // warp-uniform
-      float* yp = a.y + (long long)b * a.y_bstride + ((tq * TN + tl) * ytst_ + ytoff_);
-      float* sst = sstat + ((it & 1) * 8 + ewi) * NC * 3;
-      mbar_wait(BAR(T_TFULL + buf), tph);
-      tc_fence_after();
-      for (int gi = 0; gi < ng; ++gi) {
-        const int c0 = gi * 16;
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 2 * NC + m * NC + c0), v);
-        if (gi + 1 == ng) {   // last group: the accumulator buffer is free again
-          tc_fence_before();
-          mbar_arrive(BAR(T_TEMPTY + buf));
-        }
-        const int nch = min(16, Cout_ - c0);   // warp-uniform, may be <= 0 for padded channel groups
-        const bool full = (nch == 16) && (nvalid == 32) && plain;   // warp-uniform
-        const uint32_t slot = slot_base(rp);
-        float rv[16];
-        if (has_res) {
-          // this step's copies have landed when at most D-1 newer groups are pending
-          if (D == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
-          else asm volatile("cp.async.wait_group 1;" ::: "memory");
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rv[j]) : "r"(slot + 128u * j + swz[j & 7]) : "memory");
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float r = 0.f;
-              if (tv && j < nch) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(slot + 128u * j + swz[j & 7]) : "memory");
-              rv[j] = r;
-            }
-          }
-        }
-        float* yp0 = yp + (long long)c0 * y_len_;
-        const float* bs0 = bsm + c0;
-        const unsigned ys = (unsigned)y_len_;
-        if (full) {
-          if (has_res) {
-            if (acc_ == 0) tct_rows_full<true, 0>(v, rv, bs0, yp0, ys, acc_div_);
-            else if (acc_ == 1) tct_rows_full<true, 1>(v, rv, bs0, yp0, ys, acc_div_);
-            else tct_rows_full<true, 2>(v, rv, bs0, yp0, ys, acc_div_);
-          } else {
-            if (acc_ == 0) tct_rows_full<false, 0>(v, rv, bs0, yp0, ys, acc_div_);
-            else if (acc_ == 1) tct_rows_full<false, 1>(v, rv, bs0, yp0, ys, acc_div_);
-            else tct_rows_full<false, 2>(v, rv, bs0, yp0, ys, acc_div_);
-          }
-          if (has_stats) {
-            // values back into the slot (each lane overwrites the words its residuals came from), read transposed
-#pragma unroll
-            for (int j = 0; j < 16; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + 128u * j + swz[j & 7]), "f"(v[j]) : "memory");
-            __syncwarp();
-            float x[16];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4 * k]), "=f"(x[4 * k + 1]), "=f"(x[4 * k + 2]), "=f"(x[4 * k + 3]) : "r"(slot + tsw[k]) : "memory");
-            float sum = 0.f;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) sum += x[k];
-            const float mh = sum * (1.0f / 16.0f);
-            float qh = 0.f;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) { const float d = x[k] - mh; qh = fmaf(d, d, qh); }
-            // the two halves of a channel sit in neighbouring lanes: Chan merge of two 16-sample records
-            const float mo = __shfl_xor_sync(0xffffffffu, mh, 1), qo = __shfl_xor_sync(0xffffffffu, qh, 1);
-            const float dl = mo - mh;
-            if (shalf == 0) {
-              float* sp = sst + (c0 + sch) * 3;
-              sp[0] = 32.0f; sp[1] = mh + 0.5f * dl; sp[2] = qh + qo + dl * dl * 8.0f;
-            }
-            __syncwarp();   // every lane has read the slot: it may be refilled
-          }
-        } else if (nch > 0 && nvalid > 0) {
-          if (has_res) {
-            if (acc_ == 0) tct_rows<true, 0>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-            else if (acc_ == 1) tct_rows<true, 1>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-            else tct_rows<true, 2>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-          } else {
-            if (acc_ == 0) tct_rows<false, 0>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-            else if (acc_ == 1) tct_rows<false, 1>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-            else tct_rows<false, 2>(v, rv, bs0, yp0, ys, nch, tv, out_div_, acc_div_, out_act_);
-          }
-          if (has_stats) {
-            // partial step (tail tile / channel tail / output activation): transposing shuffle tree over the valid frames,
-            // deviations from a pilot sample per channel = the value of the warp's first frame (valid when nvalid > 0)
-            if (lane == 0) {
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4)
-                *reinterpret_cast<float4*>(&pil[4 * k4]) = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const float4 p4 = *reinterpret_cast<const float4*>(&pil[4 * k4]);
-              v[4 * k4] = tv ? v[4 * k4] - p4.x : 0.f;
-              v[4 * k4 + 1] = tv ? v[4 * k4 + 1] - p4.y : 0.f;
-              v[4 * k4 + 2] = tv ? v[4 * k4 + 2] - p4.z : 0.f;
-              v[4 * k4 + 3] = tv ? v[4 * k4 + 3] - p4.w : 0.f;
-            }
-            {  // lanes L and L^16 hold the same 16 channels: the lower lane continues with the sums, the upper one with the squares
-              const bool up = (lane & 16) != 0;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float o = __shfl_xor_sync(0xffffffffu, v[i], 16);
-                v[i] = up ? fmaf(v[i], v[i], o * o) : v[i] + o;
-              }
-            }
-            xreduce_step<8>(v, lane);
-            xreduce_step<4>(v, lane);
-            xreduce_step<2>(v, lane);
-            xreduce_step<1>(v, lane);
-            // lane L < 16: S1 (sum of deviations from the pilot) of channel c0 + L; lane 16 + L: S2 (sum of their squares)
-            const float s2 = __shfl_down_sync(0xffffffffu, v[0], 16);
-            const float nn = (float)nvalid;
-            const float pl = pil[lane & 15];
-            if (lane < nch) {
-              float* sp = sst + (c0 + lane) * 3;
-              sp[0] = nn; sp[1] = pl + v[0] / nn; sp[2] = fmaxf(0.f, s2 - v[0] * v[0] / nn);
-            }
-            __syncwarp();
-          }
-        }
-        issue(tile, gi, D, rp);   // the slot is free again: the step D steps ahead
-        if (++rp == D) rp = 0;
-      }
-      if (has_stats) {
-        if (nvalid == 0) {   // this warp's frames are beyond the row: empty records for every channel
-          for (int c = lane; c < Cout_; c += 32) { sst[c * 3] = 0.f; sst[c * 3 + 1] = 0.f; sst[c * 3 + 2] = 0.f; }
-        }
-        // the four warps of an M block merge their records in fixed order: one partial per (tile, M block, channel)
-        asm volatile("bar.sync %0, 128;" ::"r"(3 + m) : "memory");
-        const int co = et & 127;
-        if (co < Cout_) {
-          float n = 0.f, mean = 0.f, m2 = 0.f;
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            const float* sp = sstat + (((it & 1) * 8 + m * 4 + qq) * NC + co) * 3;
-            const float nb = sp[0], mb = sp[1], qb = sp[2];
-            if (nb > 0.f) {
-              const float nn = n + nb, dl = mb - mean;
-              mean += dl * (nb / nn);
-              m2 += qb + dl * dl * (n * nb / nn);
-              n = nn;
-            }
-          }
-          float* gp = a.stats + (((long long)b * Cout_ + co) * a.stats_nparts + a.stats_part_offset + 2 * tq + m) * 3;
-          gp[0] = n; gp[1] = mean; gp[2] = m2;
-        }
-      }
-      if (++buf == NBUF) { buf = 0; tph ^= 1; }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (a.accum_mode != 0) tct_epilogue_role<true>(a, smem, sbase, bar0, tmem_base, ntiles, n_tq, NC, NBUF, tid, warp, lane);
+    else tct_epilogue_role<false>(a, smem, sbase, bar0, tmem_base, ntiles, n_tq, NC, NBUF, tid, warp, lane);
   }
 
   tc_fence_before();

@@ -146,7 +146,7 @@ TC_MODE_OVERRIDE = os.environ.get("ST2_TC_MODE")   # A/B testing: force one reci
 
 # Layers with at most this many output channels run the TIME-MAJOR kernel (frames on the MMA's M axis, Cout on N): HiFi-GAN's
 # C = 64 / 32 stages, conv_post.  0 disables; 128 is the kernel's limit.
-TC_TMAJOR_MAX_COUT = int(os.environ.get("ST2_TC_TMAJOR_MAX", "64"))
+TC_TMAJOR_MAX_COUT = int(os.environ.get("ST2_TC_TMAJOR_MAX", "128"))
 
 
 def _tc_mode(mode, cout=None):

@@ -154,3 +154,26 @@ def test_conv_transpose1d_tct_matches_fp32(cfg, tmajor_all):
     ca, cb = ops.adain_coef(st, torch.zeros(2, 2 * Cout, device=D))
     ea = 1 / torch.sqrt(ref.var(-1, unbiased=False) + 1e-5)
     assert maxdiff(ca, ea) / float(ea.abs().max()) < 1e-4 and maxdiff(cb, -ref.mean(-1) * ea) < 1e-3
+
+
+@pytest.mark.parametrize("C,K,L", [(32, 3, 3000), (128, 7, 1300), (64, 11, 2048)])
+def test_conv1d_tct_mrf_accumulate_plain_epilogue(C, K, L, tmajor_all):
+    """MRF mean through the accumulate modes with the plain epilogue (the full-step path that loads y one step ahead):
+    xs = (r0 + r1 + r2) / 3 with r_i = conv_i(x) + res (istftnet.py:369-375), statistics of the final sum."""
+    ops = tmajor_all
+    B = 2
+    x, res = rnd(B, C, L, seed=1), rnd(B, C, L, seed=5)
+    ws = [rnd(C, C, K, seed=10 + i, scale=1 / math.sqrt(C * K)) for i in range(3)]
+    pad = (K - 1) // 2
+    ref = sum(F.conv1d(x.double(), w.double(), None, 1, pad) + res.double() for w in ws) / 3
+    acc = torch.empty(B, C, L, device=D)
+    st = None
+    for i in range(3):
+        wd = ws[i].to(D)
+        _, st = ops.conv1d(x.to(D), ops.conv_weight_layout(wd), None, K=K, pad=pad, res=res.to(D), out=acc, accum_mode=0 if i == 0 else (2 if i == 2 else 1),
+                           accum_div=3.0, want_stats=(i == 2), wtc=ops.conv_tc_weight_layout(wd))
+    r = maxdiff(acc, ref.float()) / float(ref.abs().max())
+    assert r < 1e-4, r
+    ca, cb = ops.adain_coef(st, torch.zeros(B, 2 * C, device=D))
+    ea = 1 / torch.sqrt(ref.float().var(-1, unbiased=False) + 1e-5)
+    assert maxdiff(ca, ea) / float(ea.abs().max()) < 1e-4 and maxdiff(cb, -ref.float().mean(-1) * ea) < 1e-3
