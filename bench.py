@@ -355,8 +355,9 @@ def run_ours(args):
         "per_rank_ms_per_step": per_rank_ms,
         "stages_ms": {k_: round(v_, 3) for k_, v_ in stage_ms.items()},
         "clocks": clk,
-        "roofline": {"kernel": "st2::tc::conv1d_tc_kernel (tcgen05 implicit-GEMM Conv1d / polyphase ConvTranspose1d: fp16 high planes + e4m3 "
-                               "correction MMA, 2 MMA-times per fp32 product; 3 in the F0/N predictor)",
+        "roofline": {"kernel": "st2::tc::conv1d_tct_kernel (time-major, Cout <= 128) + st2::tc::conv1d_tc_kernel (channel-major, Cout >= 256): tcgen05 "
+                               "implicit-GEMM Conv1d / polyphase ConvTranspose1d, fp16 high planes + e4m3 correction MMA, 2 MMA-times per fp32 "
+                               "product; 3 in the F0/N predictor",
                      "bound": "tensor", "achieved": alg_tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": alg_tflops / tc_peak,
                      "frac_algorithmic": alg_tflops / tc_peak, "frac_executed": exe_tflops / tc_peak, "executed_tflops": exe_tflops,
                      "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),

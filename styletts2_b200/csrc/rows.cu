@@ -270,6 +270,76 @@ __global__ void __launch_bounds__(SM_NW * 32) linear_smallm_kernel(const float* 
 }
 
 // ------------------------------------------------------------------------------------------
+// Tiny-M Linear (M <= 8 rows, 16-byte aligned operands: the time / feature mapping MLP of the denoiser at 8 utterances per
+// GPU runs 100+ of these per step with K = 256): a warp owns TWO output features over the whole K (one float4 of each
+// weight row per lane and 128-float step, weights read once, coalesced), the 8 x 2 per-lane partial sums are folded with a
+// transposing shuffle tree (31 shuffles): lane f*8 + m ends up with (row m, feature f).  No shared memory, no block barrier,
+// 16 features per CTA; latency = two rounds of loads + the tree (the 32-row kernel above needs ~20 us for such a shape:
+// four sequential feature pairs per CTA, six of eight warps idle at K = 256).
+constexpr int TM_ROWS = 8;
+__global__ void __launch_bounds__(256) linear_tinym_kernel(const float* __restrict__ A, long long a_bs, long long a_ls, int a_L,
+                                                           const float* __restrict__ W, const float* __restrict__ bias,
+                                                           const float* __restrict__ R, long long ldr, float* __restrict__ C, long long ldc,
+                                                           int M, int Nf, int K, int act) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * 16 + warp * 2;
+  if (n0 >= Nf) return;
+  const int n1 = min(n0 + 1, Nf - 1);
+  const float* rowp[TM_ROWS];
+#pragma unroll
+  for (int m = 0; m < TM_ROWS; ++m) {
+    const int mg = min(m, M - 1);
+    const int bi = mg / a_L, l = mg - bi * a_L;
+    rowp[m] = A + (long long)bi * a_bs + (long long)l * a_ls;
+  }
+  const float* w0 = W + (long long)n0 * K;
+  const float* w1 = W + (long long)n1 * K;
+  float acc[2 * TM_ROWS];
+#pragma unroll
+  for (int i = 0; i < 2 * TM_ROWS; ++i) acc[i] = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 wa = __ldg(reinterpret_cast<const float4*>(w0 + k));
+    const float4 wb = __ldg(reinterpret_cast<const float4*>(w1 + k));
+    float4 av[TM_ROWS];
+#pragma unroll
+    for (int m = 0; m < TM_ROWS; ++m) av[m] = __ldg(reinterpret_cast<const float4*>(rowp[m] + k));
+#pragma unroll
+    for (int m = 0; m < TM_ROWS; ++m) {
+      float a0 = acc[m], a1 = acc[TM_ROWS + m];
+      a0 = fmaf(av[m].x, wa.x, a0); a0 = fmaf(av[m].y, wa.y, a0); a0 = fmaf(av[m].z, wa.z, a0); a0 = fmaf(av[m].w, wa.w, a0);
+      a1 = fmaf(av[m].x, wb.x, a1); a1 = fmaf(av[m].y, wb.y, a1); a1 = fmaf(av[m].z, wb.z, a1); a1 = fmaf(av[m].w, wb.w, a1);
+      acc[m] = a0; acc[TM_ROWS + m] = a1;
+    }
+  }
+  // lanes L and L^16 first add their 16 sums, then four halving steps leave value (lane & 15) in acc[0]
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+#define ST2_TRED(NV, OFF)                                                       \
+  {                                                                             \
+    const bool up = (lane & OFF) != 0;                                          \
+    _Pragma("unroll") for (int i = 0; i < NV / 2; ++i) {                        \
+      const float send = up ? acc[i] : acc[i + NV / 2];                         \
+      const float keep = up ? acc[i + NV / 2] : acc[i];                         \
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);                  \
+    }                                                                           \
+  }
+  ST2_TRED(16, 8) ST2_TRED(8, 4) ST2_TRED(4, 2) ST2_TRED(2, 1)
+#undef ST2_TRED
+  if (lane < 16) {
+    const int f = lane >> 3, m = lane & 7;
+    const int n = n0 + f;
+    if (n < Nf && m < M) {
+      float v = acc[0] + (bias ? bias[n] : 0.f);
+      if (act == ST2_ACT_GELU) v = gelu_erf(v);
+      else if (act == ST2_ACT_TANH) v = tanhf(v);
+      else if (act == ST2_ACT_GELU_TANH) v = gelu_tanh(v);
+      if (R) v += R[(long long)m * ldr + n];
+      C[(long long)m * ldc + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Attention (no mask), D = 64.  CTA = 4 warps, 16 queries (4 per warp); keys streamed in chunks of
 // 32 through shared memory; lane-per-key dot products, online softmax, P V through shared memory.
 constexpr int ATT_D = 64, ATT_QW = 4, ATT_WARPS = 4, ATT_KC = 32;
@@ -395,6 +465,12 @@ int st2_linear(const float* A, long long a_bs, long long a_ls, long long a_ks, i
   if (M <= 64 && a_ks == 1) {
     const bool vec = (K % 4 == 0) && (a_bs % 4 == 0) && (a_ls % 4 == 0) && ((reinterpret_cast<size_t>(A) & 15) == 0) &&
                      ((reinterpret_cast<size_t>(W) & 15) == 0);
+    if (vec && M <= TM_ROWS) {
+      linear_tinym_kernel<<<cdiv(Nf, 16), 256, 0, (cudaStream_t)stream>>>(A, a_bs, a_ls, a_L, W, bias, R, ldr, C, ldc, M, Nf, K, act);
+      ++g_launches;
+      ST2_CHECK_LAUNCH("st2_linear (tiny M)");
+      return 0;
+    }
     const int grid = cdiv(Nf, SM_NF);
     if (vec) linear_smallm_kernel<true><<<grid, SM_NW * 32, 0, (cudaStream_t)stream>>>(A, a_bs, a_ls, a_L, W, bias, R, ldr, C, ldc, M, Nf, K, act);
     else linear_smallm_kernel<false><<<grid, SM_NW * 32, 0, (cudaStream_t)stream>>>(A, a_bs, a_ls, a_L, W, bias, R, ldr, C, ldc, M, Nf, K, act);

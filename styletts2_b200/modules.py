@@ -75,7 +75,9 @@ def _maybe_wtc(w, stride, dilation, mode=TC_FAST):
     """plane-split tensor-core weight blocks when the tcgen05 conv supports the shape and it is worth it.
     mode: precision recipe (TC_FAST for the decoder / vocoder, TC_ACCURATE for the F0/N predictor)."""
     co, ci, k = w.shape
-    if stride == 1 and co >= 16 and ci >= 16 and ops.conv_tc_supported(ci, co, k, stride, dilation):
+    # Cout < 16 (conv_post of HiFi-GAN: one output channel) only through the time-major kernel, whose N is Cout rounded up to 16
+    narrow_ok = co >= 16 or (mode == TC_FAST and ops.TC_TMAJOR_MAX_COUT >= 16 and ops.TC_MODE_OVERRIDE is None)
+    if stride == 1 and narrow_ok and ci >= 16 and ops.conv_tc_supported(ci, co, k, stride, dilation):
         return ops.conv_tc_weight_layout(w, mode)
     return None
 

@@ -212,6 +212,23 @@ def test_linear_bias_gelu_residual(shape):
     assert rel(y, ref) < 1e-5, rel(y, ref)
 
 
+@pytest.mark.parametrize("shape", [(8, 256, 2048), (1, 1024, 1024), (5, 257, 1000), (8, 1024, 130), (3, 64, 18)])
+def test_linear_tiny_m(shape):
+    """M <= 8 rows (time / feature mapping MLP of the denoiser at 8 utterances per GPU): warp-per-feature-pair kernel when
+    the operands are 16-byte aligned (K % 4 == 0), the 32-row small-M kernel otherwise; odd feature counts, tanh, residual,
+    strided output rows."""
+    from styletts2_b200 import ops
+    from styletts2_b200.lib import ACT_TANH
+    M, K, Nf = shape
+    D = dev()
+    A, W, b, R = rnd(M, K, seed=1), rnd(Nf, K, seed=2, scale=1 / math.sqrt(K)), rnd(Nf, seed=3), rnd(M, Nf, seed=4)
+    ref = torch.tanh(F.linear(A.double(), W.double(), b.double())).float() + R
+    out = torch.zeros(M, Nf + 8, device=D)
+    ops.linear(A.to(D), W.to(D), b.to(D), act=ACT_TANH, R=R.to(D), out=out[:, 8:])
+    assert rel(out[:, 8:], ref) < 1e-5, rel(out[:, 8:], ref)
+    assert float(out[:, :8].abs().max()) == 0.0
+
+
 def test_linear_small_m_strided_rows():
     """small-M kernel on a column slice of a wider buffer (row stride > K) and writing into a slice"""
     from styletts2_b200 import ops
