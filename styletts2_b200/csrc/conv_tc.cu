@@ -952,15 +952,13 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
     const int k = p * 8 + ewi;
     return sbase + (uint32_t)(k < T_SLOTS_A ? SM_TRES_A + k * T_SLOT : res_b0 + (k - T_SLOTS_A) * T_SLOT);
   };
-  // byte offset of (channel j, this lane's frame) inside a slot: row j, chunk (lane / 4) ^ (j & 7), word lane & 3
-  uint32_t swz[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) swz[k] = (uint32_t)((((lane >> 2) ^ k) << 4) | ((lane & 3) << 2));
-  // transposed view for the statistics: lane -> channel lane / 2, frames 16 * (lane & 1) .. + 15 (four 16-byte chunks)
+  // byte offset of (channel j, this lane's frame) inside a slot: row j, chunk (lane / 4) ^ (j & 7), word lane & 3.  Slots are
+  // 1024-byte aligned, so the swizzle is an XOR of (j & 7) << 4 into (slot + lane_off) -- one register instead of a table.
+  const uint32_t lane_off = (uint32_t)(((lane >> 2) << 4) | ((lane & 3) << 2));
+  // transposed view for the statistics: lane -> channel lane / 2, frames 16 * (lane & 1) .. + 15 (four 16-byte chunks k:
+  // chunk ((half * 4 + k) ^ (channel & 7)) = offset t_off ^ (k << 4))
   const int sch = lane >> 1, shalf = lane & 1;
-  uint32_t tsw[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) tsw[k] = (uint32_t)(sch * 128 + ((((shalf << 2) | k) ^ (sch & 7)) << 4));
+  const uint32_t t_off = (uint32_t)(sch * 128 + ((((shalf << 2)) ^ (sch & 7)) << 4));
   if (et < 128) bsm[et] = (a.bias && et < Cout_) ? a.bias[et] : 0.f;
   asm volatile("bar.sync 5, %0;" ::"n"(NUM_EPI));
   // request the residual values of the step `ahead` steps after (tile_, gi_) into ring position p (one commit group per step,
@@ -975,19 +973,19 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
         const int tq_ = tile_ % n_tq, b_ = tile_ / n_tq;
         const int ncols_ = min(TN, Lq_ - tq_ * TN);
         const int oidx_ = (tq_ * TN + tl) * ytst_ + ytoff_;
-        const float* r0 = a.res + (long long)b_ * a.res_bstride + (long long)(gi * 16) * res_len_ + (oidx_ >> rshift_);
+        const float* r0 = a.res + (unsigned long long)(unsigned)b_ * (unsigned long long)a.res_bstride + (long long)(gi * 16) * res_len_ + (oidx_ >> rshift_);
         const uint32_t dst = slot_base(p);
         if (ncols_ - fr0 >= 32 && gi * 16 + 16 <= Cout_) {   // warp-uniform: full step
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * j + swz[j & 7]), "l"(r0) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(((dst + lane_off) ^ (uint32_t)((j & 7) << 4)) + 128u * j), "l"(r0) : "memory");
             r0 += (unsigned)res_len_;
           }
         } else if (tl < ncols_) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             if (gi * 16 + j < Cout_)
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 128u * j + swz[j & 7]), "l"(r0 + (unsigned)j * (unsigned)res_len_) : "memory");
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(((dst + lane_off) ^ (uint32_t)((j & 7) << 4)) + 128u * j), "l"(r0 + (unsigned)j * (unsigned)res_len_) : "memory");
           }
         }
       }
@@ -1008,7 +1006,7 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
       if (tile_ < ntiles) {
         const int tq_ = tile_ % n_tq, b_ = tile_ / n_tq;
         const bool tv_ = tl < min(TN, Lq_ - tq_ * TN);
-        const float* y0 = a.y + (long long)b_ * a.y_bstride + (long long)(gi * 16) * y_len_ + ((tq_ * TN + tl) * ytst_ + ytoff_);
+        const float* y0 = a.y + (unsigned long long)(unsigned)b_ * (unsigned long long)a.y_bstride + (long long)(gi * 16) * y_len_ + ((tq_ * TN + tl) * ytst_ + ytoff_);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           yon[j] = (tv_ && gi * 16 + j < Cout_) ? *y0 : 0.f;
@@ -1024,7 +1022,7 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
     const int ncols = min(TN, Lq_ - tq * TN);
     const bool tv = tl < ncols;
     const int nvalid = max(0, min(32, ncols - fr0));   // warp-uniform
-    float* yp = a.y + (long long)b * a.y_bstride + ((tq * TN + tl) * ytst_ + ytoff_);
+    float* yp = a.y + (unsigned long long)(unsigned)b * (unsigned long long)a.y_bstride + ((tq * TN + tl) * ytst_ + ytoff_);
     float* sst = sstat + ((it & 1) * 8 + ewi) * NC * 3;
     mbar_wait(BAR(T_TFULL + buf), tph);
     tc_fence_after();
@@ -1046,12 +1044,12 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
         else asm volatile("cp.async.wait_group 1;" ::: "memory");
         if (full) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rv[j]) : "r"(slot + 128u * j + swz[j & 7]) : "memory");
+          for (int j = 0; j < 16; ++j) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rv[j]) : "r"(((slot + lane_off) ^ (uint32_t)((j & 7) << 4)) + 128u * j) : "memory");
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float r = 0.f;
-            if (tv && j < nch) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(slot + 128u * j + swz[j & 7]) : "memory");
+            if (tv && j < nch) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(((slot + lane_off) ^ (uint32_t)((j & 7) << 4)) + 128u * j) : "memory");
             rv[j] = r;
           }
         }
@@ -1076,12 +1074,12 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
         if (has_stats) {
           // values back into the slot (each lane overwrites the words its residuals came from), read transposed
 #pragma unroll
-          for (int j = 0; j < 16; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + 128u * j + swz[j & 7]), "f"(v[j]) : "memory");
+          for (int j = 0; j < 16; ++j) asm volatile("st.shared.f32 [%0], %1;" ::"r"(((slot + lane_off) ^ (uint32_t)((j & 7) << 4)) + 128u * j), "f"(v[j]) : "memory");
           __syncwarp();
           float x[16];
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4 * k]), "=f"(x[4 * k + 1]), "=f"(x[4 * k + 2]), "=f"(x[4 * k + 3]) : "r"(slot + tsw[k]) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[4 * k]), "=f"(x[4 * k + 1]), "=f"(x[4 * k + 2]), "=f"(x[4 * k + 3]) : "r"((slot + t_off) ^ (uint32_t)(k << 4)) : "memory");
           float sum = 0.f;
 #pragma unroll
           for (int k = 0; k < 16; ++k) sum += x[k];

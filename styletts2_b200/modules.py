@@ -671,7 +671,7 @@ class HifiGenerator(nn.Module):
                                          alpha=self.alphas[i], res=xs, want_stats=True, wtc=up.wtc())
             x = _mrf(self.resblocks[i * nk:(i + 1) * nk], x, st, fcs, nk)
         y, _ = ops.conv1d(x, self.conv_post.wt(), self.conv_post.bias, K=7, pad=3, pre_act=ACT_SNAKE,
-                          alpha=self.alphas[self.num_upsamples], out_act=ACT_TANH)
+                          alpha=self.alphas[self.num_upsamples], out_act=ACT_TANH, wtc=self.conv_post.wtc())
         return y
 
 
