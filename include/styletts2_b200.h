@@ -111,11 +111,13 @@ int st2_conv_stats_parts(int Lq);
 #define ST2_TC_FAST 0
 #define ST2_TC_ACCURATE 1
 #define ST2_TC_F16X3 2
-/* Flag OR-ed into `mode` (FAST recipe, Cout <= 128 or Cout == 256): TIME-MAJOR weight layout and kernel -- frames on
- * the MMA's M axis (two M = 128 blocks per 256-frame tile), output channels on N = Cout rounded up to 32 (16 for Cout <=
- * 16; two blocks of 128 for Cout = 256): no tensor-pipe time or weight traffic for absent channels, epilogue stores
- * straight from the accumulator registers (a warp = 32 consecutive frames of one row), residual rows prefetched through a
- * cp.async ring.  Layout and launch must use the same mode value.  Not with dup_q0_to >= 0. */
+/* Flag OR-ed into `mode` (FAST recipe, Cout <= 128): TIME-MAJOR weight layout and kernel -- frames on the MMA's M axis
+ * (two M = 128 blocks per 256-frame tile), output channels on N = Cout rounded up to 32 (16 for Cout <= 16): no
+ * tensor-pipe time or weight traffic for absent channels, epilogue stores straight from the accumulator registers (a warp
+ * = 32 consecutive frames of one row), residual rows prefetched through a cp.async ring in shared memory, up to 8
+ * accumulators in TMEM.  Layout and launch must use the same mode value.  Not with dup_q0_to >= 0.  (Cout = 256 as two
+ * channel blocks was measured: no gain over the channel-major kernel and 3-16 % slower narrow layers from the extra tile
+ * decode -- not kept.) */
 #define ST2_TC_TMAJOR 16
 long long st2_conv_tc_weight_bytes(int Cout, int Cin, int K);
 int st2_conv_tc_weight_layout(const float* w, void* out, int Cout, int Cin, int K, int mode, void* stream);

@@ -65,8 +65,11 @@ constexpr int RWP_MAX = RW_MAX + 2;             // chunk pitch in rows of the st
 constexpr int ACT_PLANE_BYTES = KCB * RWP_MAX * 16;  // one plane of one 16-channel block
 constexpr int ACT_BUF_BYTES = 2 * ACT_PLANE_BYTES;
 constexpr int RAW_STAGES = 4;                   // cp.async ring of raw fp32 frame windows: 3 blocks (60 KB) in flight per SM
-constexpr int RAW_PITCH = 320;                  // floats per channel row of a raw block: 80 16-byte chunks >= RW_MAX + 3
-constexpr int RAW_CHUNKS = RAW_PITCH / 4;
+constexpr int RAW_CHUNKS = 80;                  // 16-byte chunks copied per channel row: 320 floats >= RW_MAX + 3
+constexpr int RAW_PITCH = 336;                  // floats per channel row of a raw block: pitch = 64 bytes mod 128, so that the 32 cp.async
+                                                // destinations of a warp (20 chunks of one row, 12 of the next) fall on distinct banks
+                                                // (ncu: 3x excess shared-memory wavefronts of the LDGSTS at a pitch of 1280 bytes; the
+                                                // shared-memory data pipe is shared with the tensor core's operand reads)
 constexpr int RAW_BYTES = CB * RAW_PITCH * 4;   // 20 KB
 constexpr int CIN_PAD_MAX = 1120;
 constexpr int NUM_STAGERS = 320;                // 10 warps (8 would not buy registers: allocation is per 4 warps, 18 -> 20)
@@ -163,8 +166,9 @@ __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cas
 // ---------------------------------------------------------------------------------------------
 // Stager inner work for one frame row (8 channels of one K chunk): AdaIN affine + activation (coefficients carry the
 // 2^6 operand scale) + plane split + shared-memory stores.  Templated on activation and recipe: no branches per element.
-//   p0 row: 8 fp16 (16 B) at chunk kc.   p1 row: MODE_FAST -> 8 + 8 e4m3 bytes (the kc-th half of the two 16-byte rows
-//   [h(z')/16 for 16 channels] and [l(z')*256 for 16 channels]);  otherwise 8 fp16 low-plane values (16 B) at chunk kc.
+//   p0 row: 8 fp16 (16 B) at chunk kc.   p1 row: MODE_FAST -> 16 e4m3 bytes at chunk kc: [h(z')/16 | l(z')*256] of the 8 channels
+//   (the order of the 32 K elements of the correction MMA is free as long as the weights use the same one: one conflict-free
+//   128-bit store per row instead of two 64-bit halves);  otherwise 8 fp16 low-plane values (16 B) at chunk kc.
 template <int ACT, int MODE>
 __device__ __forceinline__ void stage_row(const float (&x)[8], const float (&pa)[8], const float (&pb)[8], const float (&al)[8],
                                           const float (&ia)[8], float slope, bool inb, uint8_t* p0, uint8_t* p1, int kc, int r,
@@ -206,8 +210,7 @@ __device__ __forceinline__ void stage_row(const float (&x)[8], const float (&pa)
       const uint32_t f1 = __nv_cvt_float2_to_fp8x2(make_float2(lo[4 * q + 2] * F8_XLO, lo[4 * q + 3] * F8_XLO), __NV_SATFINITE, __NV_E4M3);
       l8[q] = f0 | (f1 << 16);
     }
-    *reinterpret_cast<uint2*>(p1 + (size_t)r * 16 + kc * 8) = make_uint2(h8[0], h8[1]);
-    *reinterpret_cast<uint2*>(p1 + (size_t)(RWP + r) * 16 + kc * 8) = make_uint2(l8[0], l8[1]);
+    *reinterpret_cast<uint4*>(p1 + (size_t)(kc * RWP + r) * 16) = make_uint4(h8[0], h8[1], l8[0], l8[1]);
   } else {
     const float ls = (MODE == MODE_ACC) ? ACC_LO_SCALE : 1.0f;
     uint32_t lp[4];
@@ -832,9 +835,7 @@ conv1d_tc_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int
 // (62 shuffles per 32 channels for the sum and the sum of squares of the deviation from a pilot sample), the four warps of an
 // M block merge their (count, mean, M2) records through shared memory in fixed order: two partials per tile like the
 // channel-major kernel.  FAST recipe only.
-__host__ __device__ __forceinline__ int tmajor_nc(int Cout) { return Cout <= 16 ? 16 : (Cout >= 128 ? 128 : ((Cout + 31) & ~31)); }
-// wider layers (Cout a multiple of 128) run as Cout / 128 output-channel blocks of NC = 128: tile = (utterance, block, 256 frames)
-__host__ __device__ __forceinline__ int tmajor_ncob(int Cout) { return Cout <= 128 ? 1 : Cout / 128; }
+__host__ __device__ __forceinline__ int tmajor_nc(int Cout) { return Cout <= 16 ? 16 : ((Cout + 31) & ~31); }
 
 // Shared memory of the time-major kernel: the weight ring uses 8 KB stages (the first half of the channel-major ring), the
 // second half and whatever the statistics scratch ([2 tile parities][8 warps][NC][3] floats) leaves of the epilogue area hold
@@ -842,8 +843,8 @@ __host__ __device__ __forceinline__ int tmajor_ncob(int Cout) { return Cout <= 1
 constexpr int T_WSTAGE = 8192;                            // bytes per weight stage: 8 taps (NC = 16) .. 1 tap (NC = 128)
 constexpr int SM_TRES_A = SM_W + W_STAGES * T_WSTAGE;     // 12 residual slots in the unused half of the weight ring
 constexpr int T_SLOT = 2048, T_SLOTS_A = (W_STAGES * (W_STAGE_BYTES - T_WSTAGE)) / T_SLOT;
-constexpr int SM_TBIAS = SM_EPI;                          // 256 floats (Cout <= 256)
-constexpr int SM_TPILOT = SM_TBIAS + 1024;                // [8 warps][32] floats
+constexpr int SM_TBIAS = SM_EPI;                          // 128 floats
+constexpr int SM_TPILOT = SM_TBIAS + 512;                 // [8 warps][32] floats
 constexpr int SM_TSTAT = SM_TPILOT + 8 * 32 * 4;          // [2][8][NC][3] floats, then residual slots up to SM_BAR
 static_assert(SM_TSTAT + 2 * 8 * 128 * 3 * 4 <= SM_BAR, "time-major epilogue scratch");
 static_assert(T_SLOTS_A + (SM_BAR - SM_TSTAT - 2 * 8 * 128 * 3 * 4) / T_SLOT >= 16, "two residual steps per warp in flight for NC = 128");
@@ -921,8 +922,8 @@ constexpr int T_TFULL = 16, T_TEMPTY = 24, T_MAXBUF = 8;   // barrier slots of t
 // full step are loaded one step ahead into registers (a read at the point of use would expose the HBM latency 16 times per step).
 template <bool HAS_ACC>
 __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_t* smem, const uint32_t sbase, const uint32_t bar0,
-                                                  const uint32_t tmem_base, const int ntiles, const int n_tq, const int n_cob, const int NC,
-                                                  const int NBUF, const int tid, const int warp, const int lane) {
+                                                  const uint32_t tmem_base, const int ntiles, const int n_tq, const int NC, const int NBUF,
+                                                  const int tid, const int warp, const int lane) {
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   // ================================================================ epilogue (8 warps): warp -> (M block, 32 frames)
   // The work of a warp is the sequence of (tile, 16-channel group) steps of its frames.  The residual values of a step
@@ -961,7 +962,7 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
   // chunk ((half * 4 + k) ^ (channel & 7)) = offset t_off ^ (k << 4))
   const int sch = lane >> 1, shalf = lane & 1;
   const uint32_t t_off = (uint32_t)(sch * 128 + ((((shalf << 2)) ^ (sch & 7)) << 4));
-  bsm[et] = (a.bias && et < Cout_) ? a.bias[et] : 0.f;   // 256 epilogue threads, Cout <= 256
+  if (et < 128) bsm[et] = (a.bias && et < Cout_) ? a.bias[et] : 0.f;
   asm volatile("bar.sync 5, %0;" ::"n"(NUM_EPI));
   // request the residual values of the step `ahead` steps after (tile_, gi_) into ring position p (one commit group per step,
   // also when there is nothing to copy, so that the group count identifies the step)
@@ -972,13 +973,12 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
       const int gi = s_ - dt * ng;
       tile_ += dt * (int)gridDim.x;
       if (tile_ < ntiles) {
-        const int tq_ = tile_ % n_tq, rr_ = tile_ / n_tq, cob_ = rr_ % n_cob, b_ = rr_ / n_cob;
+        const int tq_ = tile_ % n_tq, b_ = tile_ / n_tq;
         const int ncols_ = min(TN, Lq_ - tq_ * TN);
         const int oidx_ = (tq_ * TN + tl) * ytst_ + ytoff_;
-        const int ch0_ = cob_ * 128 + gi * 16;     // first channel of the step
-        const float* r0 = a.res + (unsigned long long)(unsigned)b_ * (unsigned long long)a.res_bstride + (long long)ch0_ * res_len_ + (oidx_ >> rshift_);
+        const float* r0 = a.res + (unsigned long long)(unsigned)b_ * (unsigned long long)a.res_bstride + (long long)(gi * 16) * res_len_ + (oidx_ >> rshift_);
         const uint32_t dst = slot_base(p);
-        if (ncols_ - fr0 >= 32 && ch0_ + 16 <= Cout_) {   // warp-uniform: full step
+        if (ncols_ - fr0 >= 32 && gi * 16 + 16 <= Cout_) {   // warp-uniform: full step
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(((dst + lane_off) ^ (uint32_t)((j & 7) << 4)) + 128u * j), "l"(r0) : "memory");
@@ -987,7 +987,7 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
         } else if (tl < ncols_) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            if (ch0_ + j < Cout_)
+            if (gi * 16 + j < Cout_)
               asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(((dst + lane_off) ^ (uint32_t)((j & 7) << 4)) + 128u * j), "l"(r0 + (unsigned)j * (unsigned)res_len_) : "memory");
           }
         }
@@ -1007,13 +1007,12 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
       const int gi = s_ - dt * ng;
       tile_ += dt * (int)gridDim.x;
       if (tile_ < ntiles) {
-        const int tq_ = tile_ % n_tq, rr_ = tile_ / n_tq, cob_ = rr_ % n_cob, b_ = rr_ / n_cob;
+        const int tq_ = tile_ % n_tq, b_ = tile_ / n_tq;
         const bool tv_ = tl < min(TN, Lq_ - tq_ * TN);
-        const int ch0_ = cob_ * 128 + gi * 16;
-        const float* y0 = a.y + (unsigned long long)(unsigned)b_ * (unsigned long long)a.y_bstride + (long long)ch0_ * y_len_ + ((tq_ * TN + tl) * ytst_ + ytoff_);
+        const float* y0 = a.y + (unsigned long long)(unsigned)b_ * (unsigned long long)a.y_bstride + (long long)(gi * 16) * y_len_ + ((tq_ * TN + tl) * ytst_ + ytoff_);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          yon[j] = (tv_ && ch0_ + j < Cout_) ? *y0 : 0.f;
+          yon[j] = (tv_ && gi * 16 + j < Cout_) ? *y0 : 0.f;
           y0 += (unsigned)y_len_;
         }
       }
@@ -1022,12 +1021,11 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
   load_y(blockIdx.x, 0, 0);
   int it = 0, buf = 0, tph = 0, rp = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int tq = tile % n_tq, rr = tile / n_tq, cob = rr % n_cob, b = rr / n_cob;
-    const int cb0 = cob * 128;                         // first output channel of this tile's block
+    const int tq = tile % n_tq, b = tile / n_tq;
     const int ncols = min(TN, Lq_ - tq * TN);
     const bool tv = tl < ncols;
     const int nvalid = max(0, min(32, ncols - fr0));   // warp-uniform
-    float* yp = a.y + (unsigned long long)(unsigned)b * (unsigned long long)a.y_bstride + (long long)cb0 * y_len_ + ((tq * TN + tl) * ytst_ + ytoff_);
+    float* yp = a.y + (unsigned long long)(unsigned)b * (unsigned long long)a.y_bstride + ((tq * TN + tl) * ytst_ + ytoff_);
     float* sst = sstat + ((it & 1) * 8 + ewi) * NC * 3;
     mbar_wait(BAR(T_TFULL + buf), tph);
     tc_fence_after();
@@ -1039,7 +1037,7 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
         tc_fence_before();
         mbar_arrive(BAR(T_TEMPTY + buf));
       }
-      const int nch = min(16, Cout_ - cb0 - c0);   // warp-uniform, may be <= 0 for padded channel groups
+      const int nch = min(16, Cout_ - c0);   // warp-uniform, may be <= 0 for padded channel groups
       const bool full = (nch == 16) && (nvalid == 32) && plain;   // warp-uniform
       const uint32_t slot = slot_base(rp);
       float rv[16];
@@ -1060,7 +1058,7 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
         }
       }
       float* yp0 = yp + (long long)c0 * y_len_;
-      const float* bs0 = bsm + cb0 + c0;
+      const float* bs0 = bsm + c0;
       const unsigned ys = (unsigned)y_len_;
       if (full) {
         if (HAS_ACC) {
@@ -1159,12 +1157,12 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
     }
     if (has_stats) {
       if (nvalid == 0) {   // this warp's frames are beyond the row: empty records for every channel
-        for (int c = lane; c < min(NC, Cout_ - cb0); c += 32) { sst[c * 3] = 0.f; sst[c * 3 + 1] = 0.f; sst[c * 3 + 2] = 0.f; }
+        for (int c = lane; c < Cout_; c += 32) { sst[c * 3] = 0.f; sst[c * 3 + 1] = 0.f; sst[c * 3 + 2] = 0.f; }
       }
       // the four warps of an M block merge their records in fixed order: one partial per (tile, M block, channel)
       asm volatile("bar.sync %0, 128;" ::"r"(3 + m) : "memory");
       const int co = et & 127;
-      if (co < NC && cb0 + co < Cout_) {
+      if (co < Cout_) {
         float n = 0.f, mean = 0.f, m2 = 0.f;
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
@@ -1177,7 +1175,7 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
             n = nn;
           }
         }
-        float* gp = a.stats + (((long long)b * Cout_ + cb0 + co) * a.stats_nparts + a.stats_part_offset + 2 * tq + m) * 3;
+        float* gp = a.stats + (((long long)b * Cout_ + co) * a.stats_nparts + a.stats_part_offset + 2 * tq + m) * 3;
         gp[0] = n; gp[1] = mean; gp[2] = m2;
       }
     }
@@ -1188,7 +1186,7 @@ __device__ __forceinline__ void tct_epilogue_role(const st2_conv_args& a, uint8_
 
 __global__ void __launch_bounds__(THREADS, 1)
 conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const int ncb, const int RW, const int ntiles, const int n_tq,
-                  const int NC, const int n_cob) {
+                  const int NC) {
   constexpr int MODE = MODE_FAST;
   const int RWP = RW + 2;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1273,12 +1271,12 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
     }
   } else if (warp == 1) {
     // ================================================================ weight producer (1-D TMA bulk copies)
-    if (lane == 0) weight_producer_role(wtc, sbase, bar0, ncb, K, wstep, tps, T_WSTAGE, ntiles, n_tq, n_cob);
+    if (lane == 0) weight_producer_role(wtc, sbase, bar0, ncb, K, wstep, tps, T_WSTAGE, ntiles, n_tq, 1);
   } else if (warp < 2 + NUM_STAGERS / 32) {
-    stager_role<MODE>(a, smem, sbase, bar0, ncb, RW, ntiles, n_tq, n_cob, tid, warp, lane);
+    stager_role<MODE>(a, smem, sbase, bar0, ncb, RW, ntiles, n_tq, 1, tid, warp, lane);
   } else {
-    if (a.accum_mode != 0) tct_epilogue_role<true>(a, smem, sbase, bar0, tmem_base, ntiles, n_tq, n_cob, NC, NBUF, tid, warp, lane);
-    else tct_epilogue_role<false>(a, smem, sbase, bar0, tmem_base, ntiles, n_tq, n_cob, NC, NBUF, tid, warp, lane);
+    if (a.accum_mode != 0) tct_epilogue_role<true>(a, smem, sbase, bar0, tmem_base, ntiles, n_tq, NC, NBUF, tid, warp, lane);
+    else tct_epilogue_role<false>(a, smem, sbase, bar0, tmem_base, ntiles, n_tq, NC, NBUF, tid, warp, lane);
   }
 
   tc_fence_before();
@@ -1290,7 +1288,7 @@ conv1d_tct_kernel(const st2_conv_args a, const uint4* __restrict__ wtc, const in
 
 // One element of a weight stage block [plane 2][chunk 2][rows][16 B] (rows = 128, or NC for the time-major layout): byte index -> value.
 //   plane 0: fp16 high plane of w' = w * 2^12, chunk = channels 8*kc .. 8*kc+7 (2 bytes each).
-//   plane 1, ST2_TC_FAST: e4m3 bytes; chunk 0 = l(w') * 2^4 for the block's 16 channels, chunk 1 = h(w') * 2^-8.
+//   plane 1, ST2_TC_FAST: e4m3 bytes; chunk c = [l(w') * 2^4 | h(w') * 2^-8] of channels 8c .. 8c+7 (the order stage_row uses).
 //   plane 1, otherwise:   fp16 low plane l(w') (* 2^8 for ST2_TC_ACCURATE).
 __device__ __forceinline__ void weight_stage_store(uint8_t* blk, int byte_in_stage, int mode, const float* wrow16 /* 16 channel values of this row */,
                                                    int rows) {
@@ -1306,9 +1304,10 @@ __device__ __forceinline__ void weight_stage_store(uint8_t* blk, int byte_in_sta
     if (plane == 1) o = __float2half_rn((wv - __half2float(h)) * (mode == MODE_ACC ? ACC_LO_SCALE : 1.0f));
     *reinterpret_cast<__half*>(blk + byte_in_stage) = o;
   } else {
-    const float wv = wrow16[within] * W_SCALE;
+    // chunk c, byte b: channel 8c + (b & 7); bytes 0-7 meet h(z') (-> l(w') * 2^4), bytes 8-15 meet l(z') (-> h(w') * 2^-8)
+    const float wv = wrow16[chunk * 8 + (within & 7)] * W_SCALE;
     const float hf = __half2float(__float2half_rn(wv));
-    const float val = (chunk == 0) ? (wv - hf) * F8_WLO : hf * F8_WHI;
+    const float val = (within < 8) ? (wv - hf) * F8_WLO : hf * F8_WHI;
     blk[byte_in_stage] = (uint8_t)__nv_cvt_float_to_fp8(val, __NV_SATFINITE, __NV_E4M3);
   }
 }
@@ -1316,7 +1315,7 @@ __device__ __forceinline__ void weight_stage_store(uint8_t* blk, int byte_in_sta
 // Row `col` of output-channel block `cob` -> output channel (or -1): channel-major layout spreads the channels over the four
 // TMEM lane quarters (rows_per_quarter), the time-major layout (rows = NC, one block) is the identity.
 __device__ __forceinline__ int weight_row_channel(int Cout, int cob, int col, bool tmajor) {
-  if (tmajor) return (cob * 128 + col) < Cout ? cob * 128 + col : -1;   // one block of NC rows for Cout <= 128, else blocks of 128
+  if (tmajor) return col < Cout ? col : -1;
   const int rq = rows_per_quarter(Cout, cob);
   const int qq = col >> 5, rr = col & 31;
   const int co = cob * TM + qq * rq + rr;
@@ -1447,13 +1446,13 @@ constexpr int TMAJOR = ST2_TC_TMAJOR;   // flag bit of `mode`: time-major weight
 // bytes of the weight blocks of one stride-1 convolution in the layout `mode` asks for
 static long long weight_bytes_mode(int Cout, int Cin, int K, int mode) {
   const int ncb = cdiv(Cin, CB);
-  if (mode & TMAJOR) return (long long)K * tmajor_ncob(Cout) * ncb * 64 * tmajor_nc(Cout);
+  if (mode & TMAJOR) return (long long)K * ncb * 64 * tmajor_nc(Cout);
   return (long long)K * cdiv(Cout, TM) * ncb * W_STEP_BYTES;
 }
 
 static int launch_tc(const st2_conv_args& a, const void* wtc, int mode, int max_ctas, cudaStream_t st) {
   const bool tmajor = (mode & TMAJOR) != 0;
-  const int n_tq = cdiv(a.Lq, TN), n_cob = tmajor ? tmajor_ncob(a.Cout) : cdiv(a.Cout, TM), ncb = cdiv(a.Cin, CB);
+  const int n_tq = cdiv(a.Lq, TN), n_cob = tmajor ? 1 : cdiv(a.Cout, TM), ncb = cdiv(a.Cin, CB);
   const int rw = (TN + (a.K - 1) * a.dil + 7) & ~7;
   const int ntiles = a.B * n_cob * n_tq;
   static int num_sms[64] = {0};   // per device ordinal (cudaFuncSetAttribute is per device too)
@@ -1469,7 +1468,7 @@ static int launch_tc(const st2_conv_args& a, const void* wtc, int mode, int max_
   }
   int grid = ntiles < num_sms[dev] ? ntiles : num_sms[dev];
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  if (tmajor) conv1d_tct_kernel<<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, tmajor_nc(a.Cout), n_cob);
+  if (tmajor) conv1d_tct_kernel<<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, tmajor_nc(a.Cout));
   else if (mode == MODE_FAST) conv1d_tc_kernel<MODE_FAST><<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
   else if (mode == MODE_ACC) conv1d_tc_kernel<MODE_ACC><<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
   else conv1d_tc_kernel<MODE_X3><<<grid, THREADS, SM_TOTAL, st>>>(a, (const uint4*)wtc, ncb, rw, ntiles, n_tq, n_cob);
@@ -1489,18 +1488,18 @@ long long st2_conv_tc_weight_bytes(int Cout, int Cin, int K) {
   return (long long)K * n_cob * ncb * tc::W_STEP_BYTES;   // upper bound for every layout (the time-major one is smaller)
 }
 
-// recipes 0..2; the time-major flag only with the FAST recipe and Cout <= 128 (one channel block) or Cout == 256 (two)
+// recipes 0..2; the time-major flag only with the FAST recipe and Cout <= 128 (one accumulator pair per tile)
 static bool tc_mode_ok(int mode, int Cout) {
   const int base = mode & ~tc::TMAJOR;
   if (!(base == ST2_TC_FAST || base == ST2_TC_ACCURATE || base == ST2_TC_F16X3)) return false;
-  if (mode & tc::TMAJOR) return base == ST2_TC_FAST && (Cout <= 128 || Cout == 256);
+  if (mode & tc::TMAJOR) return base == ST2_TC_FAST && Cout <= 128;
   return true;
 }
 
 int st2_conv_tc_weight_layout(const float* w, void* out, int Cout, int Cin, int K, int mode, void* stream) {
   ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0 && tc_mode_ok(mode, Cout), "st2_conv_tc_weight_layout", "bad args");
   const bool tm = (mode & tc::TMAJOR) != 0;
-  const int n_cob = tm ? tc::tmajor_ncob(Cout) : cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB), rows = tm ? tc::tmajor_nc(Cout) : tc::TM;
+  const int n_cob = tm ? 1 : cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB), rows = tm ? tc::tmajor_nc(Cout) : tc::TM;
   tc::conv_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)out, Cout, Cin, K, n_cob, ncb, mode & ~tc::TMAJOR,
                                                                              rows, tm ? 1 : 0);
   ++g_launches;
@@ -1547,7 +1546,7 @@ int st2_convT_tc_weight_layout(const float* w, void* out, int Cin, int Cout, int
   ST2_REQUIRE(w && out && Cout > 0 && Cin > 0 && K > 0 && S > 0 && tc_mode_ok(mode, Cout), "st2_convT_tc_weight_layout", "bad args");
   const int J = (K + S - 1) / S;
   const bool tm = (mode & tc::TMAJOR) != 0;
-  const int n_cob = tm ? tc::tmajor_ncob(Cout) : cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB), rows = tm ? tc::tmajor_nc(Cout) : tc::TM;
+  const int n_cob = tm ? 1 : cdiv(Cout, tc::TM), ncb = cdiv(Cin, tc::CB), rows = tm ? tc::tmajor_nc(Cout) : tc::TM;
   tc::convT_tc_weight_layout_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, (uint8_t*)out, Cin, Cout, K, S, P, J, n_cob, ncb,
                                                                               mode & ~tc::TMAJOR, rows, tm ? 1 : 0);
   ++g_launches;

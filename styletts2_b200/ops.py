@@ -145,14 +145,13 @@ TC_MODE_OVERRIDE = os.environ.get("ST2_TC_MODE")   # A/B testing: force one reci
 
 
 # Layers with at most this many output channels run the TIME-MAJOR kernel (frames on the MMA's M axis, Cout on N): HiFi-GAN's
-# C = 64 / 32 stages, conv_post, and -- faster there too -- the C = 128 / 256 resblock convs.  0 disables; the kernel takes
-# Cout <= 128 (one block of N = Cout rounded up) and Cout = 256 (two blocks of 128).
-TC_TMAJOR_MAX_COUT = int(os.environ.get("ST2_TC_TMAJOR_MAX", "256"))
+# C = 64 / 32 stages, conv_post, and -- faster there too -- the C = 128 resblock convs.  0 disables; 128 is the kernel's limit.
+TC_TMAJOR_MAX_COUT = int(os.environ.get("ST2_TC_TMAJOR_MAX", "128"))
 
 
 def _tc_mode(mode, cout=None):
     m = int(TC_MODE_OVERRIDE) if TC_MODE_OVERRIDE is not None else int(mode)
-    if cout is not None and m == TC_FAST and cout <= TC_TMAJOR_MAX_COUT and (cout <= 128 or cout == 256):
+    if cout is not None and m == TC_FAST and cout <= min(TC_TMAJOR_MAX_COUT, 128):
         m |= TC_TMAJOR
     return m
 

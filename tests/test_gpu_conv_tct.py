@@ -24,7 +24,7 @@ def rnd(*shape, seed=0, scale=1.0):
 @pytest.fixture()
 def tmajor_all(monkeypatch):
     from styletts2_b200 import ops
-    monkeypatch.setattr(ops, "TC_TMAJOR_MAX_COUT", 256)
+    monkeypatch.setattr(ops, "TC_TMAJOR_MAX_COUT", 128)
     monkeypatch.setattr(ops, "TC_MIN_WORK", 0)      # the tiny cases must not fall back to the FP32-pipe kernel
     return ops
 
@@ -46,8 +46,6 @@ TCT_CASES = [
     (2, 22, 128, 1, 1, 2403, 0),
     (1, 64, 64, 7, 1, 100, 0),       # single partial tile: M block 1 entirely beyond the row
     (2, 64, 40, 3, 1, 129, 0),       # Cout not a multiple of 8; one frame in M block 1
-    (2, 256, 256, 7, 1, 1300, 0),    # Cout = 256: two output-channel blocks of 128 per (utterance, 256 frames)
-    (2, 128, 256, 3, 3, 701, 3),     # ... few CTAs, odd length, tail tile
 ]
 
 
@@ -113,7 +111,7 @@ def test_conv1d_tct_epilogue_variants_match_channel_major(tmajor_all):
     xa = F.leaky_relu(x, 0.1)
     parts = [(F.conv1d(xa, ws[i], None, 1, 3) + res) / math.sqrt(2) for i in range(3)]
     ref = (parts[0] + parts[1] + parts[2]) / 3
-    for tmax in (256, 0):
+    for tmax in (128, 0):
         ops.TC_TMAJOR_MAX_COUT = tmax
         acc = torch.empty(B, C, L, device=D)
         for i in range(3):
@@ -122,7 +120,7 @@ def test_conv1d_tct_epilogue_variants_match_channel_major(tmajor_all):
                        accum_mode=0 if i == 0 else (2 if i == 2 else 1), accum_div=3.0, wtc=ops.conv_tc_weight_layout(wd))
         r = maxdiff(acc, ref) / float(ref.abs().max())
         assert r < 1e-4, (tmax, r)
-    ops.TC_TMAJOR_MAX_COUT = 256
+    ops.TC_TMAJOR_MAX_COUT = 128
     # tanh output activation, single output channel (HiFi-GAN conv_post, hifigan.py:344-345)
     w1, b1 = rnd(1, 32, 7, seed=20, scale=0.1), rnd(1, seed=21)
     x1 = rnd(B, 32, 5000, seed=22)
@@ -133,8 +131,7 @@ def test_conv1d_tct_epilogue_variants_match_channel_major(tmajor_all):
     assert maxdiff(y1, ref1) < 1e-4
 
 
-@pytest.mark.parametrize("cfg", [(128, 64, 6, 3, 2, 1, 1000, False), (64, 32, 4, 2, 1, 0, 2000, False), (256, 128, 12, 6, 3, 0, 700, True),
-                                 (512, 256, 20, 10, 5, 0, 300, False)])
+@pytest.mark.parametrize("cfg", [(128, 64, 6, 3, 2, 1, 1000, False), (64, 32, 4, 2, 1, 0, 2000, False), (256, 128, 12, 6, 3, 0, 700, True)])
 def test_conv_transpose1d_tct_matches_fp32(cfg, tmajor_all):
     ops = tmajor_all
     from styletts2_b200.lib import ACT_LRELU, TC_TMAJOR
@@ -159,7 +156,7 @@ def test_conv_transpose1d_tct_matches_fp32(cfg, tmajor_all):
     assert maxdiff(ca, ea) / float(ea.abs().max()) < 1e-4 and maxdiff(cb, -ref.mean(-1) * ea) < 1e-3
 
 
-@pytest.mark.parametrize("C,K,L", [(32, 3, 3000), (128, 7, 1300), (64, 11, 2048), (256, 3, 777)])
+@pytest.mark.parametrize("C,K,L", [(32, 3, 3000), (128, 7, 1300), (64, 11, 2048)])
 def test_conv1d_tct_mrf_accumulate_plain_epilogue(C, K, L, tmajor_all):
     """MRF mean through the accumulate modes with the plain epilogue (the full-step path that loads y one step ahead):
     xs = (r0 + r1 + r2) / 3 with r_i = conv_i(x) + res (istftnet.py:369-375), statistics of the final sum."""

@@ -49,15 +49,19 @@ if __name__ == "__main__":
         (32, 128, 22, 7, 1, 61441, False), (32, 22, 128, 1, 1, 61441, False),
         (8, 128, 128, 3, 1, 61441, True), (8, 128, 128, 7, 1, 61441, True), (8, 128, 128, 11, 1, 61441, True),
         (8, 128, 128, 3, 1, 51200, True), (8, 128, 128, 7, 1, 51200, True),
-        (32, 256, 256, 3, 1, 10240, True), (32, 256, 256, 7, 1, 10240, True), (32, 256, 256, 11, 1, 10240, True),
     ]
+    if os.environ.get("TCT_TM_ONLY"):   # A/B runs of kernel variants: the time-major column only
+        for (B, Cin, Cout, K, d, L, res) in shapes:
+            ms = timeit(setup(B, Cin, Cout, K, d, L, res, 128))
+            print(f"B{B} ci{Cin} co{Cout} k{K} d{d} L{L} res={int(res)}: {ms:.3f} ms", flush=True)
+        sys.exit(0)
     if len(sys.argv) > 1:
         shapes = [tuple(int(v) for v in sys.argv[1:7]) + (True,)]
     for (B, Cin, Cout, K, d, L, res) in shapes:
         fl = 2.0 * B * Cin * Cout * K * L
         by = 4.0 * B * L * (Cin + Cout * (2 if res else 1))
         row = f"B{B} ci{Cin} co{Cout} k{K} d{d} L{L} res={int(res)}  ({fl / 1e9:.1f} GFLOP, {by / 1e6:.0f} MB):"
-        for tmax, name in ((0, "channel-major"), (256, "time-major")):
+        for tmax, name in ((0, "channel-major"), (128, "time-major")):
             ms = timeit(setup(B, Cin, Cout, K, d, L, res, tmax))
             row += f"  {name} {ms:.3f} ms ({fl / ms / 1e9:.0f} TF/s fp32-eq, {by / ms / 1e6:.0f} GB/s)"
         print(row, flush=True)

@@ -8,6 +8,6 @@ from tct_bench import setup, timeit
 
 if __name__ == "__main__":
     B, Cin, Cout, K, d, L = [int(v) for v in sys.argv[1:7]]
-    tmax = int(sys.argv[7]) if len(sys.argv) > 7 else 256
+    tmax = int(sys.argv[7]) if len(sys.argv) > 7 else 128
     ms = timeit(setup(B, Cin, Cout, K, d, L, True, tmax), 3)
     print(f"B{B} ci{Cin} co{Cout} K{K} d{d} L{L} tmax{tmax}: {ms:.3f} ms")
