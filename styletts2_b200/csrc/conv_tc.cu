@@ -36,6 +36,10 @@
 //    partial statistics (count, mean, M2) exactly like the SIMT kernel.
 //  * Warp roles: warp 0 = TMEM alloc + single-thread MMA issue, warp 1 = weight TMA producer,
 //    warps 2-11 = activation stagers, warps 12-19 = epilogue.  Persistent CTAs (one per SM) loop over tiles.
+//
+// TWO kernels share the stager and weight-producer roles (device functions below): the channel-major conv1d_tc_kernel
+// described above (Cout >= 256, ACCURATE / F16X3 recipes) and the TIME-MAJOR conv1d_tct_kernel further down (FAST recipe,
+// Cout <= 128: frames on the MMA's M axis, output channels on N; its header comment has the mapping).
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 
